@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the LAPF step-2 hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] ...               # the reference algorithm on host cores
+
+Workload (BASELINE.json configs[2], the single-GPU throughput configuration): 65,536 independent
+walkers per GPU spread over 100 synthetic NIRC2-like epochs, 64 x 64 stamps, 2-body model.
+One "step" = ``--updates-per-step`` Gibbs updates of every walker (default 64 = 4 sweeps of the
+16 parameters), recording one chain row per sweep.  Metric: pixel-model evaluations per second
+(= Gibbs updates/s x pixels per stamp); Gibbs updates/s is reported next to it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+HEADER = {"itime": 1.0, "coadds": 1, "multisam": 1, "sampmode": 2}
+METRIC = "pixel_model_evals_per_sec"
+UNIT = "pixel-evals/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--walkers", type=int, default=65536, help="walkers per GPU")
+    ap.add_argument("--frames", type=int, default=100)
+    ap.add_argument("--stamp", type=int, default=64, choices=[32, 64, 128])
+    ap.add_argument("--nbody", type=int, default=2, choices=[2, 3])
+    ap.add_argument("--updates-per-step", type=int, default=64)
+    ap.add_argument("--thin", type=int, default=16)
+    ap.add_argument("--seed", type=int, default=2019)
+    ap.add_argument("--cpu-updates", type=int, default=12000, help="updates per CPU walker in the baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("config3: %d walkers/GPU x %d epochs, %dx%d stamps, %d-body, %d updates/step"
+            % (a.walkers, a.frames, a.stamp, a.stamp, a.nbody, a.updates_per_step))
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU side (the reference algorithm through the oracle port; the only place bench.py runs oracle/)
+# ----------------------------------------------------------------------------------------------
+def _cpu_walker(job):
+    """One host walker: the float64 numpy restatement of the reference loop on one stamp."""
+    nbody, size, n_updates, seed = job
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from olpefit_b200 import synth
+    from oracle import lapf_oracle as orc
+    lay = orc.layout_for(nbody)
+    ox, oy = synth.stamp_origin(size, nbody)
+    img32, _ = synth.make_frame(0, nbody, region=(oy, oy + size, ox, ox + size))
+    img = img32.astype(np.float64)
+    w = orc.weight_map(img, HEADER)
+    guess = synth.step1_guess(img32, nbody, origin=(ox, oy))
+    g_local = guess - np.array([ox, oy] * nbody + [ox, oy], dtype=np.float64)
+    p0 = orc.initial_parameters(img, g_local, lay)
+    p0[0:2 * nbody:2] += ox
+    p0[1:2 * nbody:2] += oy
+    t0 = time.perf_counter()
+    res = orc.run_chain(img, w, lay, p0, orc.NumpyStream(seed), origin=(ox, oy), n_updates=n_updates, burn_in=0)
+    return time.perf_counter() - t0, res.n_updates
+
+
+def cpu_walkers(nbody, size, n_updates, cores):
+    """``cores`` walkers in ``cores`` processes (one process per walker, like one MPI rank per
+    walker, apf_step2.py:54-57).  Returns (seconds of the slowest walker, total updates)."""
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    jobs = [(nbody, size, n_updates, 1000 + i) for i in range(cores)]
+    t0 = time.perf_counter()
+    with cf.ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
+        out = list(ex.map(_cpu_walker, jobs))
+    wall = time.perf_counter() - t0
+    return max(t for t, _ in out), sum(n for _, n in out), wall
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(1, a.cpu_updates // 4)
+    times = []
+    for i in range(a.warmup + a.steps):
+        t, n, _ = cpu_walkers(a.nbody, a.stamp, per_step, cores)
+        if i >= a.warmup:
+            times.append(t)
+    total_updates = per_step * cores * a.steps
+    secs = sum(times)
+    val = total_updates * a.stamp * a.stamp / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "gibbs_updates_per_sec": total_updates / secs,
+        "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d host walkers (one process each) x %d updates per step on epoch 0, "
+                                   "%dx%d stamp, float64 numpy restatement of apf_step2.py:300-351 "
+                                   "(the reference itself is Python 2 + astropy and cannot run here)"
+                                   % (cores, per_step, a.stamp, a.stamp)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.path = None
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as fh:
+            for ln in fh:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU side
+# ----------------------------------------------------------------------------------------------
+def run_b200(a):
+    cpu = None
+    world_env = int(os.environ.get("WORLD_SIZE", 1))
+    if world_env == 1 and not a.no_cpu_baseline:
+        # before CUDA is touched in this process; rank 0 at N=1 only
+        cores = os.cpu_count() or 1
+        t, n, wall = cpu_walkers(a.nbody, a.stamp, a.cpu_updates, cores)
+        cpu = {"value": n * a.stamp * a.stamp / t, "unit": UNIT, "cores": cores, "kind": "port",
+               "updates_per_sec": n / t, "seconds": round(wall, 2),
+               "sample": "%d host walkers (one process each, numpy float64 restatement of "
+                         "apf_step2.py:300-351) x %d updates on epoch 0, %dx%d stamp"
+                         % (cores, a.cpu_updates, a.stamp, a.stamp)}
+
+    import ctypes as C
+    import torch
+    from olpefit_b200 import _lib, dist, frame, sampler, synth
+
+    rank, local_rank, world = dist.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+
+    W, F, S, U = a.walkers, a.frames, a.stamp, a.updates_per_step
+    P = 3 * a.nbody + 10
+    stamps, origins = synth.make_stamps(F, S, a.nbody)
+    frame_of = (np.arange(W) % F).astype(np.int32)
+    p_frame = []
+    for f in range(F):
+        g = synth.step1_guess(stamps[f], a.nbody, origin=tuple(origins[f]))
+        p_frame.append(frame.initial_parameters(stamps[f], g, a.nbody, origin=tuple(origins[f])))
+    init = np.asarray(p_frame)[frame_of]
+
+    # pinned host copies: what a caller of the public API starts from
+    frames_h = torch.from_numpy(stamps).pin_memory()
+    init_h = torch.from_numpy(init).pin_memory()
+    fo_h = torch.from_numpy(frame_of).pin_memory()
+
+    def make_sampler(seed_offset=0):
+        dom = frame.prepare_domain(frames_h.to(dev, non_blocking=True), HEADER, origin=origins, nbody=a.nbody)
+        s = sampler.GibbsSampler(dom, init_h.to(dev, non_blocking=True), fo_h.to(dev, non_blocking=True),
+                                 seed=a.seed + seed_offset, burn_in=0, thin=a.thin,
+                                 id_base=rank * W, id_stride=1)
+        return dom, s
+
+    dom, smp = make_sampler()
+    rows = smp.rows_for(U)
+    chain = torch.empty((max(rows, 1), W, P + 1), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    for _ in range(a.warmup):
+        smp.run(U, out=chain)
+    torch.cuda.synchronize()
+    dist.barrier()
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    launches0 = smp.launches
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(a.steps):
+        flush.zero_()                       # evict stamps/state from L2 between timed steps
+        ev[i][0].record()
+        smp.run(U, out=chain)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    gpu_launches = smp.launches - launches0
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    ms = float(dist.allreduce_max(torch.tensor([ms], dtype=torch.float64, device=dev)).item())
+    clk = clocks.stop() if clocks else None
+
+    # cross-rank acceptance statistics (the only collective on this path), outside the timed region
+    st = smp.stats(moments=False)
+    tries, accepts, min_tries = dist.allreduce_stats(st["tries"], st["accepts"], st["min_tries"])
+    acc_rate = (accepts.double() / tries.double().clamp(min=1)).cpu().numpy()
+
+    secs = ms * 1e-3
+    updates = float(W) * U * a.steps * world
+    value = updates * S * S / secs
+
+    # ---- end to end through the public API, host buffers in, host buffers out --------------
+    e2e = None
+    if not a.no_e2e:
+        chain_h = torch.empty((max(rows, 1), W, P + 1), dtype=torch.float64).pin_memory()
+        tot_h = torch.empty((2 * P + 1,), dtype=torch.int64).pin_memory()
+        h2d = frames_h.numel() * 4 + init_h.numel() * 8 + fo_h.numel() * 4
+        d2h = chain_h.numel() * 8 + tot_h.numel() * 8
+        n_e2e = max(2, min(a.steps, 5))
+        times = []
+        for i in range(n_e2e + 1):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            d2, s2 = make_sampler(seed_offset=i + 1)
+            ch = s2.run(U, out=chain)
+            chain_h.copy_(ch, non_blocking=True)
+            stt = s2.stats(moments=False)
+            tot_h.copy_(torch.cat([stt["tries"], stt["accepts"], stt["min_tries"].reshape(1)]), non_blocking=True)
+            torch.cuda.synchronize()
+            s2.close()
+            dist.barrier()
+            if i > 0:
+                times.append(time.perf_counter() - t0)
+            del d2, s2
+        t_e2e = float(dist.allreduce_max(torch.tensor([sum(times)], dtype=torch.float64, device=dev)).item())
+        e2e = {"value": float(W) * U * n_e2e * world * S * S / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * t_e2e / n_e2e, "steps": n_e2e,
+               "what": "pinned host frames+initial parameters -> H2D -> frame prep -> sampler create -> "
+                       "%d updates -> chain rows + counters D2H to pinned host -> destroy; wall clock" % U}
+
+    smp.close()
+    if rank != 0:
+        return
+
+    # ---- roofline: SFU (MUFU.EX2) issue rate, measured on this device ------------------------
+    pk = (C.c_double * 4)()
+    _lib.check(lib.lapf_measure_peaks(pk))
+    K = 2 * a.nbody
+    per_gpu = value / world
+    ex2_rate = per_gpu * K
+    sm_count = int(pk[3])
+    f_run = (clk or {}).get("sm_mhz") or pk[2]
+    nominal_run = sm_count * 16 * f_run * 1e6
+    nominal_max = sm_count * 16 * pk[2] * 1e6
+    roofline = {
+        "bound": "sfu", "kernel": "gibbs_kernel<%d,%d>" % (a.nbody, S),
+        "achieved": ex2_rate / 1e9, "peak": pk[0] / 1e9, "unit": "Gex2/s", "frac": ex2_rate / pk[0],
+        "peak_source": "measured on this device by lapf_measure_peaks (dependent-free ex2.approx stream); "
+                       "MEASURED_PEAKS.json has no SFU entry",
+        "peak_nominal_at_run_clock": nominal_run / 1e9, "frac_nominal_at_run_clock": ex2_rate / nominal_run,
+        "peak_nominal_at_max_clock": nominal_max / 1e9, "frac_nominal_at_max_clock": ex2_rate / nominal_max,
+        "fp32_lane_ops_per_s_measured": pk[1],
+        "fp32_frac": per_gpu * (4 * K + 3) / pk[1],
+        "algorithmic": "%d ex2 + %d FP32 instructions per pixel-model evaluation" % (K, 4 * K + 3),
+        "traffic": None,
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "gibbs_updates_per_sec": updates / secs,
+        "config": {"workload": workload_name(a), "walkers_per_gpu": W, "frames": F, "stamp": S,
+                   "nbody": a.nbody, "updates_per_step": U, "thin": a.thin,
+                   "l2": "flushed between timed steps (256 MiB memset outside the event pairs); stamps are "
+                         "re-staged from HBM into shared memory by TMA in every launch",
+                   "timing": "CUDA events around each step on the launch stream, summed; max over ranks",
+                   "wall_ms_per_step_incl_flush": 1e3 * t_wall / a.steps},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(gpu_launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "acceptance_rate_mean": float(np.mean(acc_rate)), "min_tries": int(min_tries.item()),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

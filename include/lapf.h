@@ -1,0 +1,165 @@
+/*
+ * liblapf -- C ABI of the B200-native LAPF step-2 hot path.
+ *
+ * The reference (logan-pearce/olpefit) has no FFI of its own: it is a set of Python
+ * scripts whose hot loop calls two in-process functions per Gibbs update,
+ *     model = build_analytical_model(parameters_proposal)      apf_step2.py:314 (def :106-124)
+ *     chi   = chi_squared(image_nanmask, model_proposal, err)   apf_step2.py:316 (def :134-137)
+ * inside `while np.min(total_tries) < accept_min:` (apf_step2.py:300-351).  This header puts
+ * the boundary at exactly those two seams: a stateless batched model+chi-square operator and
+ * a whole-loop sampler object.  The Python binding a maintainer would add is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every entry point returns 0 (LAPF_OK) or a negative lapf_status; nothing throws;
+ *     lapf_last_error() returns a thread-local description of the last failure;
+ *   - all pointers marked "device" are CUDA device pointers owned by the caller
+ *     (e.g. torch tensors: tensor.data_ptr()); `stream` is a cudaStream_t passed as void*;
+ *   - calls are asynchronous on `stream` unless stated otherwise;
+ *   - there is NO CPU fallback: without an sm_100 device every compute call fails.
+ *
+ * Parameter vectors use the reference layouts, in FRAME pixel coordinates (0-based,
+ * x = column, y = row):
+ *   2-body, P = 16 (apf_step2.py:108):  xcs ycs xcc ycc dx dy amps ampc ampratio bkgd
+ *                                       sigmax sigmay sigmax2 sigmay2 theta theta2
+ *   3-body, P = 19 (3body/apf_step2_3body.py:108-109,266-288): xca yca xcb ycb xcc ycc dx dy
+ *                                       ampa ampb ampc ampratio bkgd sigmax sigmay sigmax2
+ *                                       sigmay2 theta theta2
+ */
+#ifndef LAPF_H
+#define LAPF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAPF_ABI_VERSION 1
+#define LAPF_MAX_PARAMS 19
+
+typedef enum lapf_status {
+    LAPF_OK = 0,
+    LAPF_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+    LAPF_ERR_CUDA = -2,         /* a CUDA runtime call failed (see lapf_last_error) */
+    LAPF_ERR_NO_DEVICE = -3,    /* no sm_100 device: there is no CPU path */
+    LAPF_ERR_NOMEM = -4
+} lapf_status;
+
+/* The pixel domain: F frames (epochs), each an ny x nx cut-out ("stamp") or a full frame.
+ * Replaces the module-level image_nanmask / err arrays of apf_step2.py:188,210: `weight` is
+ * 1/err^2 with 0 on masked pixels, so chi2 = sum weight * (data - model)^2. */
+typedef struct lapf_problem {
+    int32_t nbody;          /* 2 (apf_step2 / apf_step2a) or 3 (apf_step2_3body) */
+    int32_t ny, nx;         /* rows, columns of every frame */
+    int32_t n_frames;       /* F */
+    int32_t floor_index;    /* parameter slot added as the constant floor: 12 reproduces the
+                               reference for both layouts (apf_step2.py:120 -- sigmax2 --
+                               and 3body/apf_step2_3body.py:121 -- bkgd) */
+    int32_t reserved;
+    const float* data;      /* device [F][ny][nx]; finite everywhere (0 on masked pixels) */
+    const float* weight;    /* device [F][ny][nx] */
+    const int32_t* origin;  /* device [F][2]: frame coordinates (x0, y0) of pixel [0][0] */
+} lapf_problem;
+
+/* Configuration of a batch of independent walkers (replaces "one MPI rank per walker",
+ * apf_step2.py:54-57).  Walker i of this batch has global id id_base + i * id_stride; the
+ * random stream of a walker depends only on (seed, global id, update index), so results do
+ * not depend on how walkers are sharded over GPUs. */
+typedef struct lapf_config {
+    lapf_problem problem;
+    int64_t n_walkers;
+    int64_t id_base, id_stride;
+    uint64_t seed;
+    const int32_t* frame_of;    /* device [n_walkers] frame index per walker, or NULL (frame 0) */
+    const double* init_params;  /* device [n_walkers][P] starting point (apf_step2.py:247-273) */
+    const double* widths;       /* HOST [P] jump widths, or NULL for the reference table
+                                   (apf_step2.py:234 / 3body:220-238) */
+    int64_t burn_in;            /* chain rows are produced once count >= burn_in (apf_step2.py:342) */
+    int32_t thin;               /* keep every thin-th row after burn-in (1 = reference) */
+    int32_t team_warps;         /* warps cooperating on one walker: 0 = choose automatically */
+} lapf_config;
+
+typedef struct lapf_sampler lapf_sampler;
+
+int lapf_abi_version(void);
+const char* lapf_last_error(void);
+
+/* Number of parameters (16 / 19) for nbody, or a negative status. */
+int lapf_num_params(int nbody);
+/* Copies the reference jump widths / log10-proposal flags for nbody into out[P]. */
+int lapf_default_widths(int nbody, double* widths_out, int32_t* is_log_out);
+
+/* K1 -- build_analytical_model + chi_squared (apf_step2.py:106-137) for B parameter vectors.
+ *   params     device [B][P] double
+ *   frame_of   device [B] or NULL (all vectors use frame 0)
+ *   model_out  device [B][ny][nx] float or NULL
+ *   chi2_out   device [B] double or NULL */
+int lapf_model_chi2(const lapf_problem* prob, const double* params, int64_t B,
+                    const int32_t* frame_of, float* model_out, double* chi2_out, void* stream);
+
+/* K2 -- the sampler loop (apf_step2.py:276-351).  create() copies init_params, evaluates the
+ * initial chi-square (apf_step2.py:283-289) and zeroes the try/accept counters (:276). */
+int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream);
+int lapf_sampler_destroy(lapf_sampler* s);
+
+/* Chain rows a run of n_updates starting at the sampler's current count will produce. */
+int64_t lapf_sampler_rows_for(const lapf_sampler* s, int64_t n_updates);
+
+/* Advance every walker by n_updates Gibbs updates (one proposed parameter each).
+ *   chain_out  device [rows][n_walkers][P+1] double (P parameters then chi-square, the column
+ *              order of <rank>_finalarray_mpi.csv, apf_step2.py:346-351), or NULL to record
+ *              nothing; rows_cap = capacity in rows (must be >= lapf_sampler_rows_for). */
+int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int64_t rows_cap,
+                     void* stream);
+
+/* Current state: state_out device [n_walkers][P+1] double; counters device [n_walkers][P]
+ * uint32 each (total_tries / total_accept of apf_step2.py:276,304,323).  Any may be NULL. */
+int lapf_sampler_state(lapf_sampler* s, double* state_out, uint32_t* tries_out,
+                       uint32_t* accepts_out, void* stream);
+
+/* K4 -- batch statistics, written to device memory:
+ *   totals_out  device int64[2P+1]: sum over walkers of tries[P], accepts[P], then the minimum
+ *               over walkers and parameters of tries (stop rule of apf_step2.py:300, globalised)
+ *   moments_out device double[F][P+1][3] or NULL: per frame and column, over that frame's
+ *               walkers: sum of chain means, sum of squared chain means, sum of chain variances
+ *               of the rows recorded so far (the ingredients of apf_step3.py:265-276)
+ *   counts_out  device int64[F+1] or NULL: walkers per frame, then rows recorded per walker */
+int lapf_sampler_stats(lapf_sampler* s, int64_t* totals_out, double* moments_out,
+                       int64_t* counts_out, void* stream);
+
+/* Total update count so far (same for every walker). */
+int64_t lapf_sampler_count(const lapf_sampler* s);
+/* Kernel launches issued by this sampler so far (for benchmark accounting). */
+int64_t lapf_sampler_launches(const lapf_sampler* s);
+
+/* K3 -- ordered device->pinned-host copy of a finished chain segment: copy_stream waits for
+ * everything queued on compute_stream, then copies nbytes.  Replaces the whole-file rewrite
+ * of apf_step2.py:355-360 as the way rows leave the sampler. */
+int lapf_chain_drain(const void* device_src, void* pinned_dst, size_t nbytes,
+                     void* compute_stream, void* copy_stream);
+
+/* Host-side writer of one walker's <rank>_finalarray_mpi.csv (apf_step2.py:357-360):
+ * a leading all-nan row, then n_rows rows of n_cols doubles taken from rows[r*row_stride + c],
+ * comma separated, CRLF terminated, shortest round-trip decimal.  Synchronous, CPU only. */
+int lapf_write_chain_csv(const char* path, const double* rows, int64_t n_rows, int32_t n_cols,
+                         int64_t row_stride, int32_t leading_nan_row);
+
+/* Frame preparation on device (apf_step2.py:176-210): saturation mask + noise map folded into
+ * the weight map, and cut-outs taken from full frames.
+ *   frames     device [F][fy][fx] float      header scalars as in the reference
+ *   origin     device [F][2] (x0, y0) of each cut-out
+ *   data_out, weight_out device [F][ny][nx] float */
+int lapf_frame_prep(const float* frames, int32_t n_frames, int32_t fy, int32_t fx,
+                    const int32_t* origin, int32_t ny, int32_t nx, double satlevel,
+                    double readnoise, float* data_out, float* weight_out, void* stream);
+
+/* Micro-benchmarks for the roofline denominators: issue rates of MUFU.EX2 and FFMA on the
+ * current device.  Synchronous.  out[0] = ex2 results/s, out[1] = FFMA lane-ops/s,
+ * out[2] = SM clock (MHz) reported by the driver, out[3] = SM count. */
+int lapf_measure_peaks(double* out4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAPF_H */

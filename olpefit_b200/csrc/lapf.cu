@@ -1,0 +1,990 @@
+// liblapf: kernels and C ABI of the B200-native LAPF step-2 hot path (see include/lapf.h).
+//
+// Kernels
+//   K1  model_chi2_stamp_kernel / model_chi2_generic_kernel   stateless model + chi-square
+//   K2  gibbs_kernel        persistent sampler: a CTA owns a staged stamp, each warp a walker
+//   K4  totals_kernel / moments_kernel                         batch statistics
+//   --  frame_prep_kernel, pack_state_kernel, peak_*_kernel
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (olpefit_b200/build.py).
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lapf.h"
+#include "lapf_device.cuh"
+
+using namespace lapf;
+
+// =============================================================================================
+// error plumbing
+// =============================================================================================
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(LAPF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),    \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+static int require_device() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(LAPF_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return fail(LAPF_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    if (major != 10)
+        return fail(LAPF_ERR_NO_DEVICE, "device has compute capability %d.x; liblapf is built for sm_100a only", major);
+    return LAPF_OK;
+}
+
+// reference tables: apf_step2.py:215-217,234 and 3body/apf_step2_3body.py:220-238,292-295
+static const double kWidths2[16] = {0.01, 0.01, 0.3, 0.3, 0.08, 0.09, 0.0025, 0.02,
+                                    0.001, 0.0008, 0.002, 0.002, 0.001, 0.001, 0.008, 0.01};
+static const double kWidths3[19] = {0.01, 0.01, 0.3, 0.3, 0.3, 0.3, 0.08, 0.09, 0.0025, 0.02,
+                                    0.02, 0.001, 0.0008, 0.002, 0.002, 0.001, 0.001, 0.008, 0.01};
+static const int kLog2[] = {6, 7, 9, 10, 11, 12, 13};
+static const int kLog3[] = {8, 9, 10, 12, 13, 14, 15, 16};
+
+static uint32_t log_mask_for(int nbody) {
+    uint32_t m = 0;
+    if (nbody == 2)
+        for (int i : kLog2) m |= 1u << i;
+    else
+        for (int i : kLog3) m |= 1u << i;
+    return m;
+}
+
+// =============================================================================================
+// K1: stateless model + chi-square
+// =============================================================================================
+struct ProbPtrs {
+    const float* data;
+    const float* weight;
+    const int32_t* origin;
+    int n_frames, floor_index;
+};
+
+template <int NB, int NX, int NY, bool STORE>
+__global__ void __launch_bounds__(128)
+model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t B,
+                        const int32_t* __restrict__ frame_of, float* __restrict__ model_out,
+                        double* __restrict__ chi2_out) {
+    constexpr int P = Layout<NB>::P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * 4 + warp;
+    if (b >= B) return;
+    const int f = frame_of ? frame_of[b] : 0;
+    if (f < 0 || f >= pr.n_frames) {
+        if (lane == 0 && chi2_out) chi2_out[b] = nan("");
+        return;
+    }
+    Coef<NB> cf;
+    set_all<NB>(cf, params + b * P, pr.origin[2 * f], pr.origin[2 * f + 1], pr.floor_index);
+    const size_t off = (size_t)f * NX * NY;
+    const double chi = warp_chi2<NB, NX, NY, STORE>(cf, pr.data + off, pr.weight + off,
+                                                    STORE ? model_out + (size_t)b * NX * NY : nullptr, lane);
+    if (lane == 0 && chi2_out) chi2_out[b] = chi;
+}
+
+// Any (ny, nx), e.g. the reference's whole 1024 x 1024 frame (apf_step2.py:94,237): grid =
+// (row tiles, B); per-tile FP64 partials are summed in a fixed order by reduce_tiles_kernel.
+// Centres are split into integer + fraction so pixel offsets stay accurate in FP32 at any
+// distance from the frame corner.
+template <int NB>
+__global__ void __launch_bounds__(256)
+model_chi2_generic_kernel(ProbPtrs pr, int ny, int nx, int rows_per_tile, const double* __restrict__ params,
+                          const int32_t* __restrict__ frame_of, float* __restrict__ model_out,
+                          double* __restrict__ partial) {
+    using L = Layout<NB>;
+    constexpr int K = 2 * NB;
+    const int64_t b = blockIdx.y;
+    const int tile = blockIdx.x, ntile = gridDim.x;
+    const int f = frame_of ? frame_of[b] : 0;
+    __shared__ double red[8];
+    if (f < 0 || f >= pr.n_frames) {
+        if (threadIdx.x == 0 && partial) partial[b * ntile + tile] = nan("");
+        return;
+    }
+    const double* pv = params + b * L::P;
+    Coef<NB> cf;
+    set_all<NB>(cf, pv, 0, 0, pr.floor_index);   // shapes, amplitudes, floor; centres redone below
+    int xi[K], yi[K];
+    float xf[K], yf[K];
+    {
+        const double dx = pv[L::I_DX], dy = pv[L::I_DY];
+        const int ox = pr.origin[2 * f], oy = pr.origin[2 * f + 1];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int o = k >> 1;
+            const double xc = pv[2 * o] - (double)ox + ((k & 1) ? dx : 0.0);
+            const double yc = pv[2 * o + 1] - (double)oy + ((k & 1) ? dy : 0.0);
+            // clamp so the int conversion is defined for wild proposals; exactness only matters nearby
+            const double fx = floor(fmin(fmax(xc, -1e9), 1e9)), fy = floor(fmin(fmax(yc, -1e9), 1e9));
+            xi[k] = (int)fx;
+            yi[k] = (int)fy;
+            xf[k] = (float)(xc - fx);
+            yf[k] = (float)(yc - fy);
+        }
+    }
+    const float* d = pr.data + (size_t)f * ny * nx;
+    const float* w = pr.weight + (size_t)f * ny * nx;
+    float* mo = model_out ? model_out + (size_t)b * ny * nx : nullptr;
+    const int r0 = tile * rows_per_tile, r1 = min(ny, r0 + rows_per_tile);
+    double acc = 0.0;
+    for (int r = r0; r < r1; ++r) {
+        float yd[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) yd[k] = (float)(r - yi[k]) - yf[k];
+        for (int c = threadIdx.x; c < nx; c += blockDim.x) {
+            float m = cf.floor;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float xd = (float)(c - xi[k]) - xf[k];
+                const float t = fmaf(cf.sa[k & 1], xd, cf.sb[k & 1] * yd[k]);
+                const float q = fmaf(xd, t, (cf.sc[k & 1] * yd[k]) * yd[k]);
+                m = fmaf(cf.amp[k], ex2_approx(q), m);
+            }
+            const size_t idx = (size_t)r * nx + c;
+            if (mo) mo[idx] = m;
+            const float res = d[idx] - m;
+            acc += (double)((w[idx] * res) * res);
+        }
+    }
+    acc = warp_sum_f64(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && partial) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        partial[b * ntile + tile] = s;
+    }
+}
+
+__global__ void reduce_tiles_kernel(const double* __restrict__ partial, int ntile, int64_t B,
+                                    double* __restrict__ chi2_out) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int t = 0; t < ntile; ++t) s += partial[b * ntile + t];
+    chi2_out[b] = s;
+}
+
+// =============================================================================================
+// K2: persistent Gibbs sampler
+// =============================================================================================
+struct RunArgs {
+    const float* data;
+    const float* weight;
+    const int32_t* origin;
+    const int32_t* item_frame;   // [n_items]
+    const int32_t* item_first;   // [n_items] offset into walker_of
+    const int32_t* item_count;   // [n_items] walkers in the item (<= warps per CTA)
+    const int32_t* walker_of;    // local walker indices grouped by frame
+    double* state;               // [W][P+1]  parameters, chi-square
+    const double* shift;         // [W][P+1]  initial state (shift of the running moments)
+    double* moments;             // [W][P+1][2] running sum / sum of squares of recorded rows
+    uint32_t* tries;             // [W][P]
+    uint32_t* accepts;           // [W][P]
+    double* chain;               // [rows][W][P+1] or nullptr
+    int64_t n_walkers;
+    int64_t t0, n_updates;       // first update index, updates in this launch
+    int64_t next_record;         // first count >= t0+1 at which a row is recorded
+    int64_t id_base, id_stride;
+    uint64_t seed;
+    double widths[LAPF_MAX_PARAMS];
+    uint32_t log_mask;
+    int thin, floor_index, n_items;
+};
+
+constexpr int kTrialStride = 20;   // doubles of per-warp scratch (P <= 19)
+
+template <int NB, int NX, int NY>
+__device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, const float* sw,
+                                           double* tv, int wl, int frame, int lane) {
+    using L = Layout<NB>;
+    constexpr int P = L::P;
+    const uint64_t gid = (uint64_t)(a.id_base + (int64_t)wl * a.id_stride);
+    const int ox = a.origin[2 * frame], oy = a.origin[2 * frame + 1];
+    double* st = a.state + (size_t)wl * (P + 1);
+
+    // lane j < P owns parameter j and its counters; lane P owns chi-square
+    double p = (lane <= P) ? st[lane] : 0.0;
+    double chi_c = shfl_f64(p, P);
+    uint32_t tr = 0, ac = 0;
+    double sh = 0.0, m1 = 0.0, m2 = 0.0;
+    if (lane < P) {
+        tr = a.tries[(size_t)wl * P + lane];
+        ac = a.accepts[(size_t)wl * P + lane];
+    }
+    if (lane <= P) {
+        sh = a.shift[(size_t)wl * (P + 1) + lane];
+        m1 = a.moments[((size_t)wl * (P + 1) + lane) * 2];
+        m2 = a.moments[((size_t)wl * (P + 1) + lane) * 2 + 1];
+    }
+
+    Coef<NB> cf;
+    if (lane < P) tv[lane] = p;
+    __syncwarp();
+    set_shape<NB>(cf, 0, (float)tv[L::I_SX], (float)tv[L::I_SY], (float)tv[L::I_TH]);
+    set_shape<NB>(cf, 1, (float)tv[L::I_SX2], (float)tv[L::I_SY2], (float)tv[L::I_TH2]);
+    float csa[2] = {cf.sa[0], cf.sa[1]}, csb[2] = {cf.sb[0], cf.sb[1]}, csc[2] = {cf.sc[0], cf.sc[1]};
+
+    int my_k = 0;
+    double my_step = 0.0, my_lnu = 0.0;
+    int64_t next_rec = a.next_record;
+    int64_t row = 0;
+
+#pragma unroll 1
+    for (int64_t u = 0; u < a.n_updates; ++u) {
+        const int slot = (int)(u & 31);
+        if (slot == 0) {
+            // lane l prepares the draws of update t0+u+l: 32 updates of random numbers at once
+            const Draw dr = make_draw(a.seed, gid, (uint64_t)(a.t0 + u + lane), P);
+            my_k = dr.k;
+            const double wz = a.widths[dr.k] * dr.z;
+            my_step = ((a.log_mask >> dr.k) & 1u) ? exp10(wz) : wz;
+            my_lnu = dr.lnu;
+        }
+        const int k = __shfl_sync(kFull, my_k, slot);                 // apf_step2.py:302
+        const double step = shfl_f64(my_step, slot);
+        const double lnu = shfl_f64(my_lnu, slot);
+        const double pk = shfl_f64(p, k);
+        // proposal (apf_step2.py:63-70): additive, or multiplicative 10^(w z) for the log10
+        // parameters; log10 of a negative value is nan there, and 0 stays 0.
+        const double nv = ((a.log_mask >> k) & 1u) ? (pk < 0.0 ? nan("") : pk * step) : pk + step;
+
+        __syncwarp();
+        if (lane < P) tv[lane] = (lane == k) ? nv : p;                // :312-313
+        __syncwarp();
+        set_centres_amps<NB>(cf, tv, ox, oy, a.floor_index);
+        cf.sa[0] = csa[0]; cf.sb[0] = csb[0]; cf.sc[0] = csc[0];
+        cf.sa[1] = csa[1]; cf.sb[1] = csb[1]; cf.sc[1] = csc[1];
+        if (k >= L::I_SX) {                                           // a shape parameter moved
+            if (k == L::I_SX2 || k == L::I_SY2 || k == L::I_TH2)
+                set_shape<NB>(cf, 1, (float)tv[L::I_SX2], (float)tv[L::I_SY2], (float)tv[L::I_TH2]);
+            else
+                set_shape<NB>(cf, 0, (float)tv[L::I_SX], (float)tv[L::I_SY], (float)tv[L::I_TH]);
+        }
+        const double chi_t = warp_chi2<NB, NX, NY, false>(cf, sd, sw, nullptr, lane);   // :314-316
+
+        // accept iff u < exp(-(chi_t - chi_c)/2) (apf_step2.py:139-148); false on nan
+        const bool acc = lnu < -0.5 * (chi_t - chi_c);
+        if (lane == k) {
+            ++tr;                                                     // :304
+            if (acc) { ++ac; p = nv; }                                // :323-325
+        }
+        if (acc) {
+            chi_c = chi_t;                                            // :327
+            csa[0] = cf.sa[0]; csb[0] = cf.sb[0]; csc[0] = cf.sc[0];
+            csa[1] = cf.sa[1]; csb[1] = cf.sb[1]; csc[1] = cf.sc[1];
+        }
+        if (a.t0 + u + 1 == next_rec) {                               // :342-351
+            if (lane <= P) {
+                const double v = (lane == P) ? chi_c : p;
+                if (a.chain) a.chain[((size_t)row * a.n_walkers + wl) * (P + 1) + lane] = v;
+                const double dl = v - sh;
+                m1 += dl;
+                m2 = fma(dl, dl, m2);
+            }
+            ++row;
+            next_rec += a.thin;
+        }
+    }
+
+    if (lane < P) {
+        st[lane] = p;
+        a.tries[(size_t)wl * P + lane] = tr;
+        a.accepts[(size_t)wl * P + lane] = ac;
+    }
+    if (lane == P) st[P] = chi_c;
+    if (lane <= P) {
+        a.moments[((size_t)wl * (P + 1) + lane) * 2] = m1;
+        a.moments[((size_t)wl * (P + 1) + lane) * 2 + 1] = m2;
+    }
+}
+
+template <int NB, int NX, int NY, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_constant__ RunArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sd = reinterpret_cast<float*>(smem_raw);
+    float* sw = sd + NX * NY;
+    double* trial = reinterpret_cast<double*>(sw + NX * NY);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(trial + NW * kTrialStride);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+
+    // contiguous share of the item list: consecutive items mostly share a frame
+    const int i0 = (int)(((int64_t)a.n_items * blockIdx.x) / gridDim.x);
+    const int i1 = (int)(((int64_t)a.n_items * (blockIdx.x + 1)) / gridDim.x);
+    int cur_frame = -1;
+    uint32_t phase = 0;
+    for (int it = i0; it < i1; ++it) {
+        const int f = a.item_frame[it];
+        if (f != cur_frame) {
+            __syncthreads();   // every warp has finished reading the previous stamp
+            if (threadIdx.x == 0) {
+                constexpr uint32_t kBytes = NX * NY * sizeof(float);
+                fence_proxy_async();
+                mbar_expect_tx(bar, 2 * kBytes);
+                tma_bulk_g2s(sd, a.data + (size_t)f * NX * NY, kBytes, bar);
+                tma_bulk_g2s(sw, a.weight + (size_t)f * NX * NY, kBytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            cur_frame = f;
+        }
+        if (warp < a.item_count[it])
+            run_walker<NB, NX, NY>(a, sd, sw, trial + warp * kTrialStride,
+                                   a.walker_of[a.item_first[it] + warp], f, lane);
+    }
+}
+
+// state[w] = (init params, chi2); shift = state; counters and moments zeroed
+__global__ void pack_state_kernel(const double* __restrict__ init, const double* __restrict__ chi, int P,
+                                  int64_t W, double* __restrict__ state, double* __restrict__ shift) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * (P + 1)) return;
+    const int64_t w = i / (P + 1);
+    const int j = (int)(i % (P + 1));
+    const double v = (j < P) ? init[w * P + j] : chi[w];
+    state[i] = v;
+    shift[i] = v;
+}
+
+// =============================================================================================
+// K4: batch statistics
+// =============================================================================================
+__global__ void totals_kernel(const uint32_t* __restrict__ tries, const uint32_t* __restrict__ accepts,
+                              int P, int64_t W, unsigned long long* __restrict__ out /*[2P+1]*/) {
+    // integer sums and a min: order-independent, so atomics are deterministic here
+    const int j = blockIdx.y;
+    unsigned long long st = 0, sa = 0, mn = ~0ull;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long t = tries[w * P + j];
+        st += t;
+        sa += accepts[w * P + j];
+        mn = min(mn, t);
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        st += __shfl_xor_sync(kFull, st, off);
+        sa += __shfl_xor_sync(kFull, sa, off);
+        mn = min(mn, __shfl_xor_sync(kFull, mn, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out + j, st);
+        atomicAdd(out + P + j, sa);
+        atomicMin(out + 2 * P, mn);
+    }
+}
+
+__global__ void totals_init_kernel(unsigned long long* out, int P) {
+    const int i = threadIdx.x;
+    if (i < 2 * P) out[i] = 0ull;
+    if (i == 2 * P) out[i] = ~0ull;
+}
+
+// One CTA per frame, one warp per column: fixed-order FP64 reduction over that frame's walkers.
+__global__ void moments_kernel(const double* __restrict__ moments, const double* __restrict__ shift,
+                               const int32_t* __restrict__ walker_of, const int32_t* __restrict__ frame_start,
+                               int P, int64_t n_rows, double* __restrict__ out /*[F][P+1][3]*/) {
+    const int f = blockIdx.x, col = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (col > P) return;
+    const int b = frame_start[f], e = frame_start[f + 1];
+    double s_mean = 0.0, s_mean2 = 0.0, s_var = 0.0;
+    if (n_rows > 0) {
+        const double inv = 1.0 / (double)n_rows;
+        for (int i = b + lane; i < e; i += 32) {
+            const size_t w = (size_t)walker_of[i];
+            const double m1 = moments[(w * (P + 1) + col) * 2] * inv;
+            const double m2 = moments[(w * (P + 1) + col) * 2 + 1] * inv;
+            const double mean = shift[w * (P + 1) + col] + m1;
+            s_mean += mean;
+            s_mean2 += mean * mean;
+            s_var += m2 - m1 * m1;     // population variance, np.std()**2 of apf_step3.py:270
+        }
+    }
+    s_mean = warp_sum_f64(s_mean);
+    s_mean2 = warp_sum_f64(s_mean2);
+    s_var = warp_sum_f64(s_var);
+    if (lane == 0) {
+        double* o = out + ((size_t)f * (P + 1) + col) * 3;
+        o[0] = s_mean;
+        o[1] = s_mean2;
+        o[2] = s_var;
+    }
+}
+
+__global__ void counts_kernel(const int32_t* __restrict__ frame_start, int F, int64_t n_rows,
+                              long long* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F) out[i] = frame_start[i + 1] - frame_start[i];
+    if (i == F) out[F] = n_rows;
+}
+
+// =============================================================================================
+// frame preparation (apf_step2.py:176-210) + cut-out
+// =============================================================================================
+__global__ void frame_prep_kernel(const float* __restrict__ frames, int F, int fy, int fx,
+                                  const int32_t* __restrict__ origin, int ny, int nx, double satcut,
+                                  double rn2, float* __restrict__ data_out, float* __restrict__ weight_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = (int64_t)F * ny * nx;
+    if (i >= n) return;
+    const int f = (int)(i / ((int64_t)ny * nx));
+    const int r = (int)((i / nx) % ny), c = (int)(i % nx);
+    const int y = origin[2 * f + 1] + r, x = origin[2 * f] + c;
+    float d = 0.f, w = 0.f;
+    if (y >= 0 && y < fy && x >= 0 && x < fx) {
+        const float v = frames[((size_t)f * fy + y) * fx + x];
+        // masked (apf_step2.py:188: image > 0.8*satlevel) or non-finite pixels get zero weight
+        if (isfinite(v) && !((double)v > satcut)) {
+            d = v;
+            w = (float)(1.0 / (rn2 + fabs((double)v)));   // 1/err^2, err^2 = readnoise^2 + |image| (:207-210)
+        }
+    }
+    data_out[i] = d;
+    weight_out[i] = w;
+}
+
+// =============================================================================================
+// roofline micro-benchmarks
+// =============================================================================================
+__global__ void __launch_bounds__(256) peak_ex2_kernel(float* out, int iters) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.1f * (float)(threadIdx.x & 7) + 0.05f * j;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = ex2_approx(-x[j]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += x[j];
+    if (s == 123.456f) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) peak_ffma_kernel(float* out, int iters, float a, float b) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.1f * (float)(threadIdx.x & 7) + 0.05f * j;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], a, b);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += x[j];
+    if (s == 123.456f) out[0] = s;
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct lapf_sampler {
+    lapf_config cfg;
+    int P = 0;
+    int device = 0;
+    int nw = 0, minb = 0, grid = 0;
+    size_t smem = 0;
+    int64_t count = 0;      // updates done so far
+    int64_t launches = 0;
+    int n_items = 0;
+    double widths[LAPF_MAX_PARAMS];
+    uint32_t log_mask = 0;
+    // device buffers owned by the handle
+    double* state = nullptr;
+    double* shift = nullptr;
+    double* moments = nullptr;
+    uint32_t* tries = nullptr;
+    uint32_t* accepts = nullptr;
+    int32_t* walker_of = nullptr;
+    int32_t* frame_start = nullptr;
+    int32_t* item_frame = nullptr;
+    int32_t* item_first = nullptr;
+    int32_t* item_count = nullptr;
+};
+
+static bool stamp_supported(int ny, int nx) { return ny == nx && (nx == 32 || nx == 64 || nx == 128); }
+
+static int check_problem(const lapf_problem* p) {
+    if (!p) return fail(LAPF_ERR_INVALID, "problem is NULL");
+    if (p->nbody != 2 && p->nbody != 3) return fail(LAPF_ERR_INVALID, "nbody must be 2 or 3, got %d", p->nbody);
+    if (p->ny <= 0 || p->nx <= 0 || p->n_frames <= 0)
+        return fail(LAPF_ERR_INVALID, "bad shape ny=%d nx=%d n_frames=%d", p->ny, p->nx, p->n_frames);
+    const int P = 3 * p->nbody + 10;
+    if (p->floor_index < 0 || p->floor_index >= P)
+        return fail(LAPF_ERR_INVALID, "floor_index %d outside [0,%d)", p->floor_index, P);
+    if (!p->data || !p->weight || !p->origin) return fail(LAPF_ERR_INVALID, "data/weight/origin must be device pointers");
+    if (((uintptr_t)p->data & 15) || ((uintptr_t)p->weight & 15))
+        return fail(LAPF_ERR_INVALID, "data and weight must be 16-byte aligned (TMA bulk copies)");
+    return LAPF_OK;
+}
+
+static int64_t rows_upto(int64_t count, int64_t burn_in, int thin) {
+    // rows recorded by updates with count' in [1, count]: count' >= burn_in and
+    // (count' - burn_in) % thin == 0 (apf_step2.py:333,342-351; thin = 1 there)
+    if (count < burn_in || count < 1) return 0;
+    int64_t n = (count - burn_in) / thin + 1;
+    if (burn_in <= 0) n -= 1;   // count' = burn_in = 0 is not an update
+    return n;
+}
+
+static int64_t next_record_after(int64_t count, int64_t burn_in, int thin) {
+    // smallest count' > count with count' >= burn_in, count' >= 1, (count' - burn_in) % thin == 0
+    int64_t c = std::max<int64_t>(count + 1, std::max<int64_t>(burn_in, 1));
+    const int64_t rem = (c - burn_in) % thin;
+    if (rem) c += thin - rem;
+    return c;
+}
+
+template <int NB, int NX, bool STORE>
+static void launch_stamp_k1(const ProbPtrs& pr, const double* params, int64_t B, const int32_t* frame_of,
+                            float* model_out, double* chi2_out, cudaStream_t st) {
+    const unsigned grid = (unsigned)((B + 3) / 4);
+    model_chi2_stamp_kernel<NB, NX, NX, STORE><<<grid, 128, 0, st>>>(pr, params, B, frame_of, model_out, chi2_out);
+}
+
+template <int NB, int NX>
+static void launch_stamp_k1_store(bool store, const ProbPtrs& pr, const double* params, int64_t B,
+                                  const int32_t* frame_of, float* model_out, double* chi2_out, cudaStream_t st) {
+    if (store)
+        launch_stamp_k1<NB, NX, true>(pr, params, B, frame_of, model_out, chi2_out, st);
+    else
+        launch_stamp_k1<NB, NX, false>(pr, params, B, frame_of, model_out, chi2_out, st);
+}
+
+template <int NB>
+static void launch_stamp_k1_size(int nx, bool store, const ProbPtrs& pr, const double* params, int64_t B,
+                                 const int32_t* frame_of, float* model_out, double* chi2_out, cudaStream_t st) {
+    if (nx == 32) launch_stamp_k1_store<NB, 32>(store, pr, params, B, frame_of, model_out, chi2_out, st);
+    else if (nx == 64) launch_stamp_k1_store<NB, 64>(store, pr, params, B, frame_of, model_out, chi2_out, st);
+    else launch_stamp_k1_store<NB, 128>(store, pr, params, B, frame_of, model_out, chi2_out, st);
+}
+
+extern "C" {
+
+int lapf_abi_version(void) { return LAPF_ABI_VERSION; }
+const char* lapf_last_error(void) { return g_err; }
+
+int lapf_num_params(int nbody) {
+    if (nbody != 2 && nbody != 3) return fail(LAPF_ERR_INVALID, "nbody must be 2 or 3, got %d", nbody);
+    return 3 * nbody + 10;
+}
+
+int lapf_default_widths(int nbody, double* widths_out, int32_t* is_log_out) {
+    const int P = lapf_num_params(nbody);
+    if (P < 0) return P;
+    const double* w = nbody == 2 ? kWidths2 : kWidths3;
+    const uint32_t m = log_mask_for(nbody);
+    for (int i = 0; i < P; ++i) {
+        if (widths_out) widths_out[i] = w[i];
+        if (is_log_out) is_log_out[i] = (m >> i) & 1u;
+    }
+    return LAPF_OK;
+}
+
+int lapf_model_chi2(const lapf_problem* prob, const double* params, int64_t B, const int32_t* frame_of,
+                    float* model_out, double* chi2_out, void* stream) {
+    int rc = check_problem(prob);
+    if (rc) return rc;
+    if (B < 0 || (B > 0 && !params)) return fail(LAPF_ERR_INVALID, "params is NULL or B < 0");
+    if (B == 0) return LAPF_OK;
+    if ((rc = require_device())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProbPtrs pr{prob->data, prob->weight, prob->origin, prob->n_frames, prob->floor_index};
+    if (stamp_supported(prob->ny, prob->nx) && (!model_out || ((uintptr_t)model_out & 15) == 0)) {
+        if (prob->nbody == 2)
+            launch_stamp_k1_size<2>(prob->nx, model_out != nullptr, pr, params, B, frame_of, model_out, chi2_out, st);
+        else
+            launch_stamp_k1_size<3>(prob->nx, model_out != nullptr, pr, params, B, frame_of, model_out, chi2_out, st);
+        CU(cudaGetLastError());
+        return LAPF_OK;
+    }
+    // generic domain (e.g. the whole frame)
+    if (B > 65535) return fail(LAPF_ERR_INVALID, "generic-domain evaluation supports B <= 65535 per call, got %lld", (long long)B);
+    const int rows_per_tile = 16;
+    const int ntile = (prob->ny + rows_per_tile - 1) / rows_per_tile;
+    double* partial = nullptr;
+    if (chi2_out) CU(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)B * ntile, st));
+    dim3 grid((unsigned)ntile, (unsigned)B);
+    if (prob->nbody == 2)
+        model_chi2_generic_kernel<2><<<grid, 256, 0, st>>>(pr, prob->ny, prob->nx, rows_per_tile, params, frame_of, model_out, partial);
+    else
+        model_chi2_generic_kernel<3><<<grid, 256, 0, st>>>(pr, prob->ny, prob->nx, rows_per_tile, params, frame_of, model_out, partial);
+    CU(cudaGetLastError());
+    if (chi2_out) {
+        reduce_tiles_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(partial, ntile, B, chi2_out);
+        CU(cudaGetLastError());
+        CU(cudaFreeAsync(partial, st));
+    }
+    return LAPF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampler
+// ---------------------------------------------------------------------------------------------
+extern "C++" {
+template <int NB, int NX, int NW, int MINB>
+static int configure_gibbs(lapf_sampler* s) {
+    auto kern = gibbs_kernel<NB, NX, NX, NW, MINB>;
+    s->nw = NW;
+    s->minb = MINB;
+    s->smem = 2 * sizeof(float) * NX * NX + sizeof(double) * NW * kTrialStride + 16;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    int per_sm = 0, sms = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, s->smem));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    if (per_sm < 1) return fail(LAPF_ERR_CUDA, "gibbs kernel does not fit on an SM");
+    s->grid = per_sm * sms;
+    return LAPF_OK;
+}
+
+template <int NB, int NX, int NW, int MINB>
+static int launch_gibbs(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
+    const int grid = std::min(s->grid, a.n_items);
+    gibbs_kernel<NB, NX, NX, NW, MINB><<<grid, NW * 32, s->smem, st>>>(a);
+    CU(cudaGetLastError());
+    return LAPF_OK;
+}
+
+#define LAPF_DISPATCH_GIBBS(FN, ...)                                                        \
+    do {                                                                                    \
+        const int nb__ = s->cfg.problem.nbody, nx__ = s->cfg.problem.nx;                    \
+        if (nb__ == 2 && nx__ == 32) return FN<2, 32, 8, 2>(__VA_ARGS__);                   \
+        if (nb__ == 2 && nx__ == 64) return FN<2, 64, 8, 2>(__VA_ARGS__);                   \
+        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 16, 1>(__VA_ARGS__);                \
+        if (nb__ == 3 && nx__ == 32) return FN<3, 32, 8, 2>(__VA_ARGS__);                   \
+        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 8, 2>(__VA_ARGS__);                   \
+        if (nb__ == 3 && nx__ == 128) return FN<3, 128, 16, 1>(__VA_ARGS__);                \
+        return fail(LAPF_ERR_INVALID, "unsupported sampler shape nbody=%d nx=%d", nb__, nx__); \
+    } while (0)
+
+static int configure_dispatch(lapf_sampler* s) { LAPF_DISPATCH_GIBBS(configure_gibbs, s); }
+static int launch_dispatch(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
+    LAPF_DISPATCH_GIBBS(launch_gibbs, s, a, st);
+}
+}  // extern "C++"
+
+static void free_sampler(lapf_sampler* s) {
+    if (!s) return;
+    cudaFree(s->state); cudaFree(s->shift); cudaFree(s->moments); cudaFree(s->tries); cudaFree(s->accepts);
+    cudaFree(s->walker_of); cudaFree(s->frame_start); cudaFree(s->item_frame); cudaFree(s->item_first);
+    cudaFree(s->item_count);
+    delete s;
+}
+
+int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream) {
+    if (!cfg || !out) return fail(LAPF_ERR_INVALID, "cfg/out is NULL");
+    *out = nullptr;
+    int rc = check_problem(&cfg->problem);
+    if (rc) return rc;
+    const lapf_problem& pb = cfg->problem;
+    if (!stamp_supported(pb.ny, pb.nx))
+        return fail(LAPF_ERR_INVALID, "sampler supports square stamps of 32, 64 or 128 pixels, got %dx%d", pb.ny, pb.nx);
+    if (cfg->n_walkers <= 0 || cfg->n_walkers > (int64_t)1 << 30)
+        return fail(LAPF_ERR_INVALID, "n_walkers %lld out of range", (long long)cfg->n_walkers);
+    if (!cfg->init_params) return fail(LAPF_ERR_INVALID, "init_params is NULL");
+    if (cfg->thin < 1) return fail(LAPF_ERR_INVALID, "thin must be >= 1");
+    if (cfg->burn_in < 0) return fail(LAPF_ERR_INVALID, "burn_in must be >= 0");
+    if (cfg->team_warps != 0 && cfg->team_warps != 1)
+        return fail(LAPF_ERR_INVALID, "team_warps %d not supported (0 or 1)", cfg->team_warps);
+    if ((rc = require_device())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    lapf_sampler* s = new (std::nothrow) lapf_sampler();
+    if (!s) return fail(LAPF_ERR_NOMEM, "out of host memory");
+    s->cfg = *cfg;
+    s->P = 3 * pb.nbody + 10;
+    const int P = s->P;
+    const int64_t W = cfg->n_walkers;
+    cudaGetDevice(&s->device);
+    const double* wsrc = cfg->widths ? cfg->widths : (pb.nbody == 2 ? kWidths2 : kWidths3);
+    for (int i = 0; i < LAPF_MAX_PARAMS; ++i) s->widths[i] = i < P ? wsrc[i] : 0.0;
+    s->cfg.widths = nullptr;
+    s->log_mask = log_mask_for(pb.nbody);
+
+#define CUS(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            free_sampler(s);                                                                       \
+            return fail(LAPF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),    \
+                        __FILE__, __LINE__);                                                       \
+        }                                                                                          \
+    } while (0)
+
+    if ((rc = configure_dispatch(s))) { free_sampler(s); return rc; }
+
+    // group walkers by frame (counting sort) and cut each frame's list into CTA-sized items
+    std::vector<int32_t> fo((size_t)W, 0);
+    if (cfg->frame_of) {
+        CUS(cudaMemcpyAsync(fo.data(), cfg->frame_of, sizeof(int32_t) * W, cudaMemcpyDeviceToHost, st));
+        CUS(cudaStreamSynchronize(st));
+    }
+    const int F = pb.n_frames;
+    std::vector<int32_t> start((size_t)F + 1, 0);
+    for (int64_t w = 0; w < W; ++w) {
+        if (fo[w] < 0 || fo[w] >= F) {
+            free_sampler(s);
+            return fail(LAPF_ERR_INVALID, "frame_of[%lld] = %d outside [0,%d)", (long long)w, fo[w], F);
+        }
+        start[fo[w] + 1]++;
+    }
+    for (int f = 0; f < F; ++f) start[f + 1] += start[f];
+    std::vector<int32_t> order((size_t)W), fill(start.begin(), start.end() - 1);
+    for (int64_t w = 0; w < W; ++w) order[fill[fo[w]]++] = (int32_t)w;
+    std::vector<int32_t> it_frame, it_first, it_count;
+    for (int f = 0; f < F; ++f)
+        for (int32_t b = start[f]; b < start[f + 1]; b += s->nw) {
+            it_frame.push_back(f);
+            it_first.push_back(b);
+            it_count.push_back(std::min<int32_t>(s->nw, start[f + 1] - b));
+        }
+    s->n_items = (int)it_frame.size();
+
+    const size_t nst = (size_t)W * (P + 1);
+    CUS(cudaMalloc((void**)&s->state, sizeof(double) * nst));
+    CUS(cudaMalloc((void**)&s->shift, sizeof(double) * nst));
+    CUS(cudaMalloc((void**)&s->moments, sizeof(double) * nst * 2));
+    CUS(cudaMalloc((void**)&s->tries, sizeof(uint32_t) * W * P));
+    CUS(cudaMalloc((void**)&s->accepts, sizeof(uint32_t) * W * P));
+    CUS(cudaMalloc((void**)&s->walker_of, sizeof(int32_t) * W));
+    CUS(cudaMalloc((void**)&s->frame_start, sizeof(int32_t) * (F + 1)));
+    CUS(cudaMalloc((void**)&s->item_frame, sizeof(int32_t) * s->n_items));
+    CUS(cudaMalloc((void**)&s->item_first, sizeof(int32_t) * s->n_items));
+    CUS(cudaMalloc((void**)&s->item_count, sizeof(int32_t) * s->n_items));
+    CUS(cudaMemcpyAsync(s->walker_of, order.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, st));
+    CUS(cudaMemcpyAsync(s->frame_start, start.data(), sizeof(int32_t) * (F + 1), cudaMemcpyHostToDevice, st));
+    CUS(cudaMemcpyAsync(s->item_frame, it_frame.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
+    CUS(cudaMemcpyAsync(s->item_first, it_first.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
+    CUS(cudaMemcpyAsync(s->item_count, it_count.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
+    CUS(cudaMemsetAsync(s->moments, 0, sizeof(double) * nst * 2, st));
+    CUS(cudaMemsetAsync(s->tries, 0, sizeof(uint32_t) * W * P, st));
+    CUS(cudaMemsetAsync(s->accepts, 0, sizeof(uint32_t) * W * P, st));
+
+    // initial chi-square (apf_step2.py:283-289) through K1, then pack the state
+    double* chi0 = nullptr;
+    CUS(cudaMallocAsync((void**)&chi0, sizeof(double) * W, st));
+    rc = lapf_model_chi2(&pb, cfg->init_params, W, cfg->frame_of, nullptr, chi0, st);
+    if (rc) { free_sampler(s); return rc; }
+    s->launches++;
+    pack_state_kernel<<<(unsigned)((nst + 255) / 256), 256, 0, st>>>(cfg->init_params, chi0, P, W, s->state, s->shift);
+    CUS(cudaGetLastError());
+    CUS(cudaFreeAsync(chi0, st));
+    // the host vectors above are pageable: make sure the copies have consumed them
+    CUS(cudaStreamSynchronize(st));
+    s->launches++;
+#undef CUS
+    *out = s;
+    return LAPF_OK;
+}
+
+int lapf_sampler_destroy(lapf_sampler* s) {
+    free_sampler(s);
+    return LAPF_OK;
+}
+
+int64_t lapf_sampler_rows_for(const lapf_sampler* s, int64_t n_updates) {
+    if (!s || n_updates < 0) return fail(LAPF_ERR_INVALID, "bad arguments");
+    return rows_upto(s->count + n_updates, s->cfg.burn_in, s->cfg.thin) -
+           rows_upto(s->count, s->cfg.burn_in, s->cfg.thin);
+}
+
+int64_t lapf_sampler_count(const lapf_sampler* s) { return s ? s->count : fail(LAPF_ERR_INVALID, "sampler is NULL"); }
+int64_t lapf_sampler_launches(const lapf_sampler* s) { return s ? s->launches : fail(LAPF_ERR_INVALID, "sampler is NULL"); }
+
+int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int64_t rows_cap, void* stream) {
+    if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
+    if (n_updates < 0) return fail(LAPF_ERR_INVALID, "n_updates < 0");
+    if (n_updates == 0) return LAPF_OK;
+    const int64_t rows = lapf_sampler_rows_for(s, n_updates);
+    if (chain_out && rows_cap < rows)
+        return fail(LAPF_ERR_INVALID, "chain_out holds %lld rows but this run records %lld", (long long)rows_cap, (long long)rows);
+    const lapf_problem& pb = s->cfg.problem;
+    RunArgs a;
+    a.data = pb.data; a.weight = pb.weight; a.origin = pb.origin;
+    a.item_frame = s->item_frame; a.item_first = s->item_first; a.item_count = s->item_count;
+    a.walker_of = s->walker_of;
+    a.state = s->state; a.shift = s->shift; a.moments = s->moments;
+    a.tries = s->tries; a.accepts = s->accepts;
+    a.chain = chain_out;
+    a.n_walkers = s->cfg.n_walkers;
+    a.t0 = s->count; a.n_updates = n_updates;
+    a.next_record = next_record_after(s->count, s->cfg.burn_in, s->cfg.thin);
+    a.id_base = s->cfg.id_base; a.id_stride = s->cfg.id_stride;
+    a.seed = s->cfg.seed;
+    memcpy(a.widths, s->widths, sizeof(a.widths));
+    a.log_mask = s->log_mask;
+    a.thin = s->cfg.thin; a.floor_index = pb.floor_index; a.n_items = s->n_items;
+    int rc = launch_dispatch(s, a, (cudaStream_t)stream);
+    if (rc) return rc;
+    s->count += n_updates;
+    s->launches++;
+    return LAPF_OK;
+}
+
+int lapf_sampler_state(lapf_sampler* s, double* state_out, uint32_t* tries_out, uint32_t* accepts_out, void* stream) {
+    if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t W = s->cfg.n_walkers;
+    if (state_out) CU(cudaMemcpyAsync(state_out, s->state, sizeof(double) * W * (s->P + 1), cudaMemcpyDeviceToDevice, st));
+    if (tries_out) CU(cudaMemcpyAsync(tries_out, s->tries, sizeof(uint32_t) * W * s->P, cudaMemcpyDeviceToDevice, st));
+    if (accepts_out) CU(cudaMemcpyAsync(accepts_out, s->accepts, sizeof(uint32_t) * W * s->P, cudaMemcpyDeviceToDevice, st));
+    return LAPF_OK;
+}
+
+int lapf_sampler_stats(lapf_sampler* s, int64_t* totals_out, double* moments_out, int64_t* counts_out, void* stream) {
+    if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = s->P;
+    const int64_t W = s->cfg.n_walkers;
+    const int64_t n_rows = rows_upto(s->count, s->cfg.burn_in, s->cfg.thin);
+    if (totals_out) {
+        totals_init_kernel<<<1, 64, 0, st>>>((unsigned long long*)totals_out, P);
+        const unsigned gx = (unsigned)std::min<int64_t>(148, (W + 255) / 256);
+        totals_kernel<<<dim3(gx, P), 256, 0, st>>>(s->tries, s->accepts, P, W, (unsigned long long*)totals_out);
+        CU(cudaGetLastError());
+        s->launches += 2;
+    }
+    if (moments_out) {
+        moments_kernel<<<s->cfg.problem.n_frames, 32 * (P + 1), 0, st>>>(s->moments, s->shift, s->walker_of,
+                                                                        s->frame_start, P, n_rows, moments_out);
+        CU(cudaGetLastError());
+        s->launches++;
+    }
+    if (counts_out) {
+        const int F = s->cfg.problem.n_frames;
+        counts_kernel<<<(F + 1 + 127) / 128, 128, 0, st>>>(s->frame_start, F, n_rows, (long long*)counts_out);
+        CU(cudaGetLastError());
+        s->launches++;
+    }
+    return LAPF_OK;
+}
+
+int lapf_chain_drain(const void* device_src, void* pinned_dst, size_t nbytes, void* compute_stream, void* copy_stream) {
+    if (!device_src || !pinned_dst) return fail(LAPF_ERR_INVALID, "NULL buffer");
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, (cudaStream_t)compute_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)copy_stream, ev, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pinned_dst, device_src, nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)copy_stream);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) return fail(LAPF_ERR_CUDA, "chain drain failed: %s", cudaGetErrorString(e));
+    return LAPF_OK;
+}
+
+int lapf_write_chain_csv(const char* path, const double* rows, int64_t n_rows, int32_t n_cols, int64_t row_stride,
+                         int32_t leading_nan_row) {
+    if (!path || (!rows && n_rows > 0) || n_cols <= 0 || n_rows < 0)
+        return fail(LAPF_ERR_INVALID, "bad arguments to lapf_write_chain_csv");
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(LAPF_ERR_INVALID, "cannot open %s for writing", path);
+    std::string buf;
+    buf.reserve(1 << 20);
+    auto put = [&](double v) {
+        if (std::isnan(v)) { buf += "nan"; return; }
+        if (std::isinf(v)) { buf += v > 0 ? "inf" : "-inf"; return; }
+        char tmp[40];
+        auto r = std::to_chars(tmp, tmp + sizeof(tmp), v);   // shortest round-trip, like repr(float)
+        buf.append(tmp, r.ptr);
+    };
+    if (leading_nan_row) {   // the seed column of apf_step2.py:278-279
+        for (int c = 0; c < n_cols; ++c) { if (c) buf += ','; buf += "nan"; }
+        buf += "\r\n";
+    }
+    bool ok = true;
+    for (int64_t r = 0; r < n_rows && ok; ++r) {
+        const double* row = rows + r * row_stride;
+        for (int c = 0; c < n_cols; ++c) { if (c) buf += ','; put(row[c]); }
+        buf += "\r\n";   // csv.writer default line terminator
+        if (buf.size() > (1 << 20) - 1024) {
+            ok = fwrite(buf.data(), 1, buf.size(), fp) == buf.size();
+            buf.clear();
+        }
+    }
+    if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), fp) == buf.size();
+    ok = (fclose(fp) == 0) && ok;
+    return ok ? LAPF_OK : fail(LAPF_ERR_INVALID, "short write to %s", path);
+}
+
+int lapf_frame_prep(const float* frames, int32_t n_frames, int32_t fy, int32_t fx, const int32_t* origin,
+                    int32_t ny, int32_t nx, double satlevel, double readnoise, float* data_out,
+                    float* weight_out, void* stream) {
+    if (!frames || !origin || !data_out || !weight_out || n_frames <= 0 || fy <= 0 || fx <= 0 || ny <= 0 || nx <= 0)
+        return fail(LAPF_ERR_INVALID, "bad arguments to lapf_frame_prep");
+    int rc = require_device();
+    if (rc) return rc;
+    const int64_t n = (int64_t)n_frames * ny * nx;
+    frame_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        frames, n_frames, fy, fx, origin, ny, nx, 0.8 * satlevel, readnoise * readnoise, data_out, weight_out);
+    CU(cudaGetLastError());
+    return LAPF_OK;
+}
+
+int lapf_measure_peaks(double* out4) {
+    if (!out4) return fail(LAPF_ERR_INVALID, "out is NULL");
+    int rc = require_device();
+    if (rc) return rc;
+    int dev = 0, sms = 0, khz = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    float* d = nullptr;
+    CU(cudaMalloc((void**)&d, 64));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    const double ops = (double)blocks * threads * (double)iters * 64.0;
+    float ms = 0.f;
+    double best[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) {
+        for (int rep = 0; rep < 4; ++rep) {   // first repetition is the warm-up
+            CU(cudaEventRecord(e0));
+            if (which == 0) peak_ex2_kernel<<<blocks, threads>>>(d, iters);
+            else peak_ffma_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+            CU(cudaEventRecord(e1));
+            CU(cudaEventSynchronize(e1));
+            CU(cudaGetLastError());
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0) best[which] = std::max(best[which], ops / (ms * 1e-3));
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    out4[0] = best[0];
+    out4[1] = best[1];
+    out4[2] = khz / 1000.0;
+    out4[3] = sms;
+    return LAPF_OK;
+}
+
+}  // extern "C"

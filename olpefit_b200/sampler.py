@@ -1,0 +1,127 @@
+"""Host-side driver of the batched Gibbs-within-Metropolis sampler (apf_step2.py:276-351).
+
+The reference runs one MPI rank per walker (apf_step2.py:54-57); here one ``GibbsSampler`` owns
+a batch of independent walkers on one GPU.  Per update and walker the device does exactly what
+the reference loop does: pick a parameter uniformly (:302), propose (:306-309), evaluate
+model + chi-square (:314-316), accept or reject (:318-327), count, and record a chain row once
+count >= burn_in (:342-351).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import PixelDomain, _stream_ptr
+
+
+class GibbsSampler:
+    def __init__(self, domain: PixelDomain, init_params, frame_of=None, *, seed=0, burn_in=0, thin=1,
+                 widths=None, id_base=0, id_stride=1, team_warps=0):
+        self.lib = _lib.load()
+        self.domain = domain
+        dev = domain.device
+        p = init_params if torch.is_tensor(init_params) else torch.as_tensor(np.asarray(init_params, dtype=np.float64))
+        p = p.to(dev, torch.float64).reshape(-1, domain.nparam).contiguous()
+        self.n_walkers = int(p.shape[0])
+        self.nparam = domain.nparam
+        fo = None
+        if frame_of is not None:
+            fo = frame_of if torch.is_tensor(frame_of) else torch.as_tensor(np.asarray(frame_of, dtype=np.int32))
+            fo = fo.to(dev, torch.int32).contiguous()
+            if fo.numel() != self.n_walkers:
+                raise ValueError("frame_of must have one entry per walker")
+        self._keep = (p, fo)   # the library copies init_params; frame_of is only read in create()
+        w_arr = None
+        if widths is not None:
+            w_np = np.ascontiguousarray(widths, dtype=np.float64)
+            if w_np.shape != (self.nparam,):
+                raise ValueError("widths must have %d entries" % self.nparam)
+            w_arr = (C.c_double * self.nparam)(*w_np.tolist())
+        cfg = _lib.Config(domain.problem(), self.n_walkers, int(id_base), int(id_stride),
+                          int(seed) & 0xFFFFFFFFFFFFFFFF, fo.data_ptr() if fo is not None else None,
+                          p.data_ptr(), w_arr, int(burn_in), int(thin), int(team_warps))
+        self.burn_in, self.thin = int(burn_in), int(thin)
+        handle = C.c_void_p()
+        _lib.check(self.lib.lapf_sampler_create(C.byref(cfg), C.byref(handle), _stream_ptr(dev)))
+        self._h = handle
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            torch.cuda.synchronize(self.domain.device)
+            self.lib.lapf_sampler_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the loop ------------------------------------------------------------------------
+    @property
+    def count(self) -> int:
+        return int(self.lib.lapf_sampler_count(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.lapf_sampler_launches(self._h))
+
+    def rows_for(self, n_updates: int) -> int:
+        return int(_lib.check(self.lib.lapf_sampler_rows_for(self._h, int(n_updates))))
+
+    def run(self, n_updates: int, record=True, out=None):
+        """Advance all walkers by ``n_updates`` updates.  Returns the chain rows recorded by this
+        call as a device tensor [rows, n_walkers, P+1] float64 (None when record is False)."""
+        rows = self.rows_for(n_updates)
+        chain = None
+        if record:
+            if out is not None:
+                if out.dtype != torch.float64 or out.numel() < rows * self.n_walkers * (self.nparam + 1):
+                    raise ValueError("out is too small for %d rows" % rows)
+                chain = out
+            else:
+                chain = torch.empty((rows, self.n_walkers, self.nparam + 1), dtype=torch.float64,
+                                    device=self.domain.device)
+        _lib.check(self.lib.lapf_sampler_run(self._h, int(n_updates),
+                                             chain.data_ptr() if chain is not None and rows > 0 else None,
+                                             rows, _stream_ptr(self.domain.device)))
+        if chain is not None and out is not None:
+            return chain.reshape(-1)[: rows * self.n_walkers * (self.nparam + 1)].view(
+                rows, self.n_walkers, self.nparam + 1)
+        return chain
+
+    def state(self):
+        """(state [W, P+1], tries [W, P], accepts [W, P]) device tensors: parameters + chi-square,
+        total_tries and total_accept of apf_step2.py:276."""
+        dev = self.domain.device
+        st = torch.empty((self.n_walkers, self.nparam + 1), dtype=torch.float64, device=dev)
+        tr = torch.empty((self.n_walkers, self.nparam), dtype=torch.int32, device=dev)
+        ac = torch.empty_like(tr)
+        _lib.check(self.lib.lapf_sampler_state(self._h, st.data_ptr(), tr.data_ptr(), ac.data_ptr(),
+                                               _stream_ptr(dev)))
+        return st, tr, ac
+
+    def stats(self, moments=True):
+        """Batch statistics reduced on the device (K4).  Returns a dict of device tensors:
+        tries[P], accepts[P], min_tries (scalar), moments [F, P+1, 3], walkers_per_frame [F],
+        rows (scalar)."""
+        dev = self.domain.device
+        pn, nf = self.nparam, self.domain.n_frames
+        tot = torch.empty((2 * pn + 1,), dtype=torch.int64, device=dev)
+        mom = torch.empty((nf, pn + 1, 3), dtype=torch.float64, device=dev) if moments else None
+        cnt = torch.empty((nf + 1,), dtype=torch.int64, device=dev)
+        _lib.check(self.lib.lapf_sampler_stats(self._h, tot.data_ptr(),
+                                               mom.data_ptr() if mom is not None else None,
+                                               cnt.data_ptr(), _stream_ptr(dev)))
+        return {"tries": tot[:pn], "accepts": tot[pn:2 * pn], "min_tries": tot[2 * pn],
+                "moments": mom, "walkers_per_frame": cnt[:nf], "rows": cnt[nf]}

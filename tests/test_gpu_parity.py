@@ -1,0 +1,287 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the numpy oracle and the
+reference-executed golden vectors.  Tolerance for the pointwise tests is the one BASELINE.json
+states: 1e-5 relative (FP32 device arithmetic vs the reference's FP64)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lapf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+HEADER = {"itime": 1.0, "coadds": 1, "multisam": 1, "sampmode": 2}
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    from olpefit_b200 import frame, model, sampler, synth
+    assert torch.cuda.is_available()
+    return {"torch": torch, "frame": frame, "model": model, "sampler": sampler, "synth": synth}
+
+
+def _domain(gpu, image, origin, nbody):
+    return gpu["frame"].prepare_domain(image, HEADER, origin=origin, nbody=nbody)
+
+
+def _random_vectors(truth_local, nbody, n, rng, spread=1.0):
+    out = []
+    for _ in range(n):
+        q = truth_local.copy()
+        q[:2 * nbody] += rng.normal(0, 1.5 * spread, 2 * nbody)
+        q[2 * nbody:2 * nbody + 2] += rng.normal(0, 0.3, 2)
+        q[2 * nbody + 2:3 * nbody + 2] *= 10 ** rng.normal(0, 0.1, nbody)
+        q[3 * nbody + 2] = rng.uniform(0.05, 0.6)
+        q[3 * nbody + 3] *= 10 ** rng.normal(0, 0.2)
+        q[3 * nbody + 4:3 * nbody + 8] *= 10 ** rng.normal(0, 0.08, 4)
+        q[3 * nbody + 8:3 * nbody + 10] = rng.uniform(-1.6, 1.6, 2)
+        # FP32-representable values, so device and oracle see identical inputs
+        out.append(q.astype(np.float32).astype(np.float64))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("nbody", [2, 3])
+def test_k1_matches_reference_executed_vectors(gpu, golden_dir, nbody):
+    z = np.load(os.path.join(golden_dir, "reference_exec_%dbody.npz" % nbody), allow_pickle=True)
+    img = z["image"]
+    dom = _domain(gpu, img, (0, 0), nbody)
+    # frame preparation on the device equals the reference's mask + error map
+    w_ref = np.where(z["mask"], 0.0, 1.0 / z["err"] ** 2)
+    np.testing.assert_allclose(dom.weight[0].cpu().numpy(), w_ref, rtol=2e-7)
+    assert np.array_equal(dom.weight[0].cpu().numpy() == 0, z["mask"])
+    model, chi2 = dom.model_chi2(z["vec_params"], want_model=True)
+    model, chi2 = model.cpu().numpy(), chi2.cpu().numpy()
+    for i in range(len(z["vec_params"])):
+        np.testing.assert_allclose(model[i], z["vec_models"][i], rtol=RTOL, atol=0)
+        assert chi2[i] == pytest.approx(z["vec_chi2"][i], rel=RTOL)
+
+
+@pytest.mark.parametrize("nbody", [2, 3])
+@pytest.mark.parametrize("size", [32, 64, 128])
+def test_k1_stamp_matches_oracle(gpu, nbody, size):
+    synth = gpu["synth"]
+    lay = orc.layout_for(nbody)
+    ox, oy = synth.stamp_origin(size)
+    img, truth = synth.make_frame(3, nbody, region=(oy, oy + size, ox, ox + size))
+    dom = _domain(gpu, img, (ox, oy), nbody)
+    w = orc.weight_map(img.astype(np.float64), HEADER)
+    tl = truth.copy()
+    tl[0:2 * nbody:2] -= ox
+    tl[1:2 * nbody:2] -= oy
+    vecs = _random_vectors(tl, nbody, 48, np.random.default_rng(7 * size + nbody))
+    vecs[:, 0:2 * nbody:2] += ox     # frame coordinates (integers added to FP32 values stay exact)
+    vecs[:, 1:2 * nbody:2] += oy
+    model, chi2 = dom.model_chi2(vecs, want_model=True)
+    model, chi2 = model.cpu().numpy(), chi2.cpu().numpy()
+    worst = 0.0
+    for i, q in enumerate(vecs):
+        m = orc.model_image(q, lay, size, size, origin=(ox, oy))
+        rel = np.max(np.abs(model[i] - m) / np.abs(m))
+        worst = max(worst, rel)
+        assert rel < RTOL
+        c = orc.chi_squared_weighted(img.astype(np.float64), m, w)
+        assert chi2[i] == pytest.approx(c, rel=RTOL)
+    # chi2-only call (no model store) gives the identical number
+    _, chi2b = dom.model_chi2(vecs, want_model=False)
+    assert np.array_equal(chi2b.cpu().numpy(), chi2)
+    print("worst per-pixel relative error S=%d nbody=%d: %.2e" % (size, nbody, worst))
+
+
+def test_k1_multi_frame_and_fix_bkgd(gpu):
+    synth = gpu["synth"]
+    lay = orc.layout_for(2)
+    size, nf = 64, 5
+    stamps, origins = synth.make_stamps(nf, size)
+    dom = gpu["frame"].prepare_domain(stamps, HEADER, origin=origins, nbody=2, floor_index=9)
+    rng = np.random.default_rng(11)
+    frame_of = rng.integers(0, nf, 40).astype(np.int32)
+    vecs = np.array([synth.truth_parameters(2, int(f)) for f in frame_of]).astype(np.float32).astype(np.float64)
+    _, chi2 = dom.model_chi2(vecs, frame_of=frame_of)
+    chi2 = chi2.cpu().numpy()
+    for i, f in enumerate(frame_of):
+        img = stamps[f].astype(np.float64)
+        m = orc.model_image(vecs[i], lay, size, size, origin=tuple(origins[f]), floor_index=9)
+        assert chi2[i] == pytest.approx(orc.chi_squared_weighted(img, m, orc.weight_map(img, HEADER)), rel=RTOL)
+
+
+@pytest.mark.parametrize("nbody", [2, 3])
+def test_k1_full_frame_matches_oracle(gpu, nbody):
+    """The reference's own pixel domain: the whole 1024 x 1024 frame (apf_step2.py:94,237)."""
+    synth = gpu["synth"]
+    lay = orc.layout_for(nbody)
+    img, truth = synth.make_frame(0, nbody)
+    dom = _domain(gpu, img, (0, 0), nbody)
+    vecs = _random_vectors(truth, nbody, 3, np.random.default_rng(5), spread=0.3)
+    vecs = np.vstack([truth.astype(np.float32).astype(np.float64)[None], vecs])
+    model, chi2 = dom.model_chi2(vecs, want_model=True)
+    model, chi2 = model.cpu().numpy(), chi2.cpu().numpy()
+    img64 = img.astype(np.float64)
+    w = orc.weight_map(img64, HEADER)
+    for i, q in enumerate(vecs):
+        m = orc.model_image(q, lay, 1024, 1024)
+        assert np.max(np.abs(model[i] - m) / np.abs(m)) < RTOL
+        assert chi2[i] == pytest.approx(orc.chi_squared_weighted(img64, m, w), rel=RTOL)
+
+
+def test_k1_ragged_domain_and_empty_batch(gpu):
+    synth = gpu["synth"]
+    lay = orc.layout_for(2)
+    ox, oy = synth.stamp_origin(64)
+    img, truth = synth.make_frame(1, 2, region=(oy, oy + 50, ox, ox + 77))   # 50 x 77: generic path
+    dom = _domain(gpu, img, (ox, oy), 2)
+    q = truth.astype(np.float32).astype(np.float64)
+    model, chi2 = dom.model_chi2(q[None], want_model=True)
+    m = orc.model_image(q, lay, 50, 77, origin=(ox, oy))
+    assert np.max(np.abs(model[0].cpu().numpy() - m) / np.abs(m)) < RTOL
+    img64 = img.astype(np.float64)
+    assert chi2.item() == pytest.approx(orc.chi_squared_weighted(img64, m, orc.weight_map(img64, HEADER)), rel=RTOL)
+    _, none = dom.model_chi2(np.zeros((0, 16)))
+    assert none.numel() == 0
+
+
+def test_k1_nan_and_degenerate_parameters(gpu):
+    """nan in, nan out (the accept rule then rejects, apf_step2.py:141-146); zero amplitude is fine."""
+    synth = gpu["synth"]
+    ox, oy = synth.stamp_origin(32)
+    img, truth = synth.make_frame(0, 2, region=(oy, oy + 32, ox, ox + 32))
+    dom = _domain(gpu, img, (ox, oy), 2)
+    a = truth.copy(); a[7] = np.nan
+    b = truth.copy(); b[10] = np.nan
+    c = truth.copy(); c[7] = c[9]          # companion amplitude equals background: zero component
+    _, chi2 = dom.model_chi2(np.array([a, b, c]))
+    chi2 = chi2.cpu().numpy()
+    assert np.isnan(chi2[0]) and np.isnan(chi2[1]) and np.isfinite(chi2[2])
+
+
+# ---------------------------------------------------------------------------------------------
+# sampler
+# ---------------------------------------------------------------------------------------------
+def _sampler_setup(gpu, nbody, size, n_frames=1):
+    synth = gpu["synth"]
+    stamps, origins = synth.make_stamps(n_frames, size, nbody)
+    dom = gpu["frame"].prepare_domain(stamps, HEADER, origin=origins, nbody=nbody)
+    guess = synth.step1_guess(stamps[0], nbody, origin=tuple(origins[0]))
+    p0 = gpu["frame"].initial_parameters(stamps[0], guess, nbody, origin=tuple(origins[0]))
+    return dom, stamps, origins, p0
+
+
+@pytest.mark.parametrize("nbody,size", [(2, 32), (2, 64), (3, 32), (2, 128)])
+def test_sampler_replays_oracle_stream(gpu, nbody, size):
+    """Same Philox stream on both sides: the device chain must follow the float64 oracle chain
+    update by update (same parameter picked, same decision, same values) until FP32 rounding of
+    chi-square flips a borderline accept -- which must not happen early."""
+    lay = orc.layout_for(nbody)
+    dom, stamps, origins, p0 = _sampler_setup(gpu, nbody, size)
+    n_upd, walkers, seed = 240, 3, 1234
+    init = np.tile(p0, (walkers, 1))
+    with gpu["sampler"].GibbsSampler(dom, init, seed=seed, burn_in=0, thin=1, id_base=5, id_stride=3) as s:
+        chain = s.run(n_upd).cpu().numpy()
+        st, tries, accepts = (t.cpu().numpy() for t in s.state())
+    img = stamps[0].astype(np.float64)
+    w = orc.weight_map(img, HEADER)
+    for wi in range(walkers):
+        stream = orc.PhiloxStream(seed, 5 + 3 * wi, lay.nparam)
+        res = orc.run_chain(img, w, lay, p0, stream, origin=tuple(origins[0]), n_updates=n_upd, burn_in=0)
+        ref = res.rows[1:]
+        dev = chain[:, wi, :]
+        same = np.all(np.isclose(dev[:, :-1], ref[:, :-1], rtol=1e-9, atol=1e-12), axis=1)
+        first_bad = int(np.argmin(same)) if not same.all() else n_upd
+        assert first_bad >= 120, "device chain left the oracle chain at update %d" % first_bad
+        np.testing.assert_allclose(dev[:first_bad, -1], ref[:first_bad, -1], rtol=RTOL)
+        if first_bad == n_upd:
+            assert np.array_equal(tries[wi], res.tries) and np.array_equal(accepts[wi], res.accepts)
+            np.testing.assert_allclose(st[wi, :-1], res.params, rtol=1e-9)
+        assert tries[wi].sum() == n_upd
+
+
+def test_sampler_initial_chi2_and_counters(gpu):
+    lay = orc.layout_for(2)
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 64)
+    img = stamps[0].astype(np.float64)
+    c0 = orc.chi_squared_weighted(img, orc.model_image(p0, lay, 64, 64, origin=tuple(origins[0])),
+                                  orc.weight_map(img, HEADER))
+    with gpu["sampler"].GibbsSampler(dom, np.tile(p0, (70, 1)), seed=9) as s:
+        st, tries, accepts = s.state()
+        assert st[:, -1].cpu().numpy() == pytest.approx(c0, rel=RTOL)     # apf_step2.py:283-289
+        assert int(tries.sum()) == 0 and int(accepts.sum()) == 0           # apf_step2.py:276
+        s.run(64, record=False)
+        st, tries, accepts = s.state()
+        assert np.all(tries.sum(dim=1).cpu().numpy() == 64)
+        assert bool((accepts <= tries).all())
+        stats = s.stats()
+        assert np.array_equal(stats["tries"].cpu().numpy(), tries.sum(dim=0).cpu().numpy())
+        assert np.array_equal(stats["accepts"].cpu().numpy(), accepts.sum(dim=0).cpu().numpy())
+        assert int(stats["min_tries"]) == int(tries.min())
+        assert s.count == 64
+
+
+def test_sampler_rows_burn_in_thin_and_split_runs(gpu):
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 32, n_frames=3)
+    torch = gpu["torch"]
+    walkers = 37
+    init = np.tile(p0, (walkers, 1))
+    frame_of = (np.arange(walkers) % 3).astype(np.int32)
+    kw = dict(seed=77, burn_in=10, thin=4)
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, **kw) as a:
+        assert a.rows_for(9) == 0 and a.rows_for(10) == 1 and a.rows_for(50) == 11
+        whole = a.run(50)
+        sa = a.state()
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, **kw) as b:
+        parts = [b.run(7), b.run(13), b.run(30)]
+        sb = b.state()
+    assert whole.shape == (11, walkers, 17)
+    assert torch.equal(whole, torch.cat(parts, dim=0))          # bitwise: launches are seamless
+    for x, y in zip(sa, sb):
+        assert torch.equal(x, y)
+    # reference rule with thin = 1 and burn-in 0: one row per update, also for rejected proposals
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, seed=77, burn_in=0, thin=1) as c:
+        assert c.run(20).shape[0] == 20
+
+
+def test_sampler_sharding_invariance(gpu):
+    """Chains depend on (seed, global walker id) only: 1 shard vs 2 interleaved shards, bitwise."""
+    torch = gpu["torch"]
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 32, n_frames=2)
+    walkers = 24
+    init = np.tile(p0, (walkers, 1))
+    frame_of = (np.arange(walkers) % 2).astype(np.int32)
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, seed=3) as s:
+        whole = s.run(40)
+    halves = []
+    for r in range(2):
+        with gpu["sampler"].GibbsSampler(dom, init[r::2], frame_of[r::2], seed=3, id_base=r, id_stride=2) as s:
+            halves.append(s.run(40))
+    assert torch.equal(whole[:, 0::2], halves[0]) and torch.equal(whole[:, 1::2], halves[1])
+
+
+def test_sampler_negative_log_parameter_is_never_accepted(gpu):
+    """log10 of a negative value is nan in the reference (apf_step2.py:67): such proposals are
+    always rejected, everything else keeps moving."""
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 32)
+    p = p0.copy()
+    p[7] = -5.0                      # companion amplitude (log10-proposed) negative
+    with gpu["sampler"].GibbsSampler(dom, p[None], seed=1) as s:
+        s.run(400, record=False)
+        st, tries, accepts = (t.cpu().numpy() for t in s.state())
+    assert tries[0, 7] > 0 and accepts[0, 7] == 0 and st[0, 7] == -5.0
+    assert accepts[0].sum() > 0 and np.isfinite(st[0, -1])
+
+
+def test_sampler_moments_match_chain(gpu):
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 32, n_frames=2)
+    walkers = 20
+    frame_of = (np.arange(walkers) % 2).astype(np.int32)
+    with gpu["sampler"].GibbsSampler(dom, np.tile(p0, (walkers, 1)), frame_of, seed=5, burn_in=20, thin=2) as s:
+        chain = s.run(200).cpu().numpy()
+        st = s.stats()
+    mom = st["moments"].cpu().numpy()
+    assert int(st["rows"]) == chain.shape[0]
+    assert st["walkers_per_frame"].cpu().numpy().tolist() == [10, 10]
+    for f in range(2):
+        sub = chain[:, frame_of == f, :]                       # [rows, walkers_f, P+1]
+        means = sub.mean(axis=0)
+        np.testing.assert_allclose(mom[f, :, 0], means.sum(axis=0), rtol=1e-10)
+        np.testing.assert_allclose(mom[f, :, 1], (means ** 2).sum(axis=0), rtol=1e-10)
+        np.testing.assert_allclose(mom[f, :, 2], (sub.std(axis=0) ** 2).sum(axis=0), rtol=1e-6, atol=1e-12)
