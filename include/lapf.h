@@ -140,10 +140,15 @@ int lapf_chain_drain(const void* device_src, void* pinned_dst, size_t nbytes,
                      void* compute_stream, void* copy_stream);
 
 /* Host-side writer of one walker's <rank>_finalarray_mpi.csv (apf_step2.py:357-360):
- * a leading all-nan row, then n_rows rows of n_cols doubles taken from rows[r*row_stride + c],
- * comma separated, CRLF terminated, shortest round-trip decimal.  Synchronous, CPU only. */
+ * optionally a leading all-nan row (the seed column of :278-279), then n_rows rows of n_cols
+ * doubles taken from rows[r*row_stride + c], comma separated, CRLF terminated (csv.writer's
+ * default dialect), shortest round-trip decimal.  Synchronous, CPU only.  With
+ * LAPF_CSV_APPEND the rows are appended, so a chain can be written segment by segment instead
+ * of the reference's whole-file rewrite every 10 updates (:355-360). */
+#define LAPF_CSV_LEADING_NAN_ROW 1
+#define LAPF_CSV_APPEND 2
 int lapf_write_chain_csv(const char* path, const double* rows, int64_t n_rows, int32_t n_cols,
-                         int64_t row_stride, int32_t leading_nan_row);
+                         int64_t row_stride, int32_t flags);
 
 /* Frame preparation on device (apf_step2.py:176-210): saturation mask + noise map folded into
  * the weight map, and cut-outs taken from full frames.

@@ -901,10 +901,12 @@ int lapf_chain_drain(const void* device_src, void* pinned_dst, size_t nbytes, vo
 }
 
 int lapf_write_chain_csv(const char* path, const double* rows, int64_t n_rows, int32_t n_cols, int64_t row_stride,
-                         int32_t leading_nan_row) {
+                         int32_t flags) {
+    const bool leading_nan_row = (flags & LAPF_CSV_LEADING_NAN_ROW) != 0;
+    const bool append = (flags & LAPF_CSV_APPEND) != 0;
     if (!path || (!rows && n_rows > 0) || n_cols <= 0 || n_rows < 0)
         return fail(LAPF_ERR_INVALID, "bad arguments to lapf_write_chain_csv");
-    FILE* fp = fopen(path, "wb");
+    FILE* fp = fopen(path, append ? "ab" : "wb");
     if (!fp) return fail(LAPF_ERR_INVALID, "cannot open %s for writing", path);
     std::string buf;
     buf.reserve(1 << 20);
