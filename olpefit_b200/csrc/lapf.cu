@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -97,11 +98,18 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
         if (lane == 0 && chi2_out) chi2_out[b] = nan("");
         return;
     }
+    __shared__ float tf[4][32];
+    const double mine = (lane < P) ? params[b * P + lane] : 0.0;
+    stage_trial<NB>(tf[warp], lane, mine, (double)pr.origin[2 * f], (double)pr.origin[2 * f + 1]);
     Coef<NB> cf;
-    set_all<NB>(cf, params + b * P, pr.origin[2 * f], pr.origin[2 * f + 1], pr.floor_index);
+    load_centres_amps<NB>(cf, tf[warp], pr.floor_index);
+    load_shape<NB>(cf, 0, tf[warp]);
+    load_shape<NB>(cf, 1, tf[warp]);
+    __shared__ __align__(16) float rt[4][NY * 4 * NB];
+    build_row_table<NB, NY>(rt[warp], cf, lane);
     const size_t off = (size_t)f * NX * NY;
-    const double chi = warp_chi2<NB, NX, NY, STORE>(cf, pr.data + off, pr.weight + off,
-                                                    STORE ? model_out + (size_t)b * NX * NY : nullptr, lane);
+    const double chi = warp_chi2<NB, NX, NY, STORE, false>(cf, rt[warp], pr.data + off, pr.weight + off,
+                                                           STORE ? model_out + (size_t)b * NX * NY : nullptr, lane);
     if (lane == 0 && chi2_out) chi2_out[b] = chi;
 }
 
@@ -126,7 +134,19 @@ model_chi2_generic_kernel(ProbPtrs pr, int ny, int nx, int rows_per_tile, const 
     }
     const double* pv = params + b * L::P;
     Coef<NB> cf;
-    set_all<NB>(cf, pv, 0, 0, pr.floor_index);   // shapes, amplitudes, floor; centres redone below
+    set_shape<NB>(cf, 0, (float)pv[L::I_SX], (float)pv[L::I_SY], (float)pv[L::I_TH]);
+    set_shape<NB>(cf, 1, (float)pv[L::I_SX2], (float)pv[L::I_SY2], (float)pv[L::I_TH2]);
+    {
+        const float ratio = (float)pv[L::I_RATIO], bkgd = (float)pv[L::I_BKGD];
+#pragma unroll
+        for (int o = 0; o < NB; ++o) {
+            const float amp = (float)pv[L::I_AMP + o] - bkgd;   // apf_step2.py:95-97
+            const float aw = amp * ratio;
+            cf.amp[2 * o] = amp - aw;
+            cf.amp[2 * o + 1] = aw;
+        }
+        cf.floor = (float)pv[pr.floor_index];
+    }
     int xi[K], yi[K];
     float xf[K], yf[K];
     {
@@ -165,8 +185,9 @@ model_chi2_generic_kernel(ProbPtrs pr, int ny, int nx, int rows_per_tile, const 
             }
             const size_t idx = (size_t)r * nx + c;
             if (mo) mo[idx] = m;
-            const float res = d[idx] - m;
-            acc += (double)((w[idx] * res) * res);
+            const float sq = sqrtf(w[idx]);
+            const float res = fmaf(-sq, m, d[idx] * sq);
+            acc += (double)(res * res);
         }
     }
     acc = warp_sum_f64(acc);
@@ -215,41 +236,28 @@ struct RunArgs {
     int thin, floor_index, n_items;
 };
 
-constexpr int kTrialStride = 20;   // doubles of per-warp scratch (P <= 19)
-
 template <int NB, int NX, int NY>
 __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, const float* sw,
-                                           double* tv, int wl, int frame, int lane) {
+                                           WarpScratch& ws, float* rt, int wl, int frame, int lane) {
     using L = Layout<NB>;
     constexpr int P = L::P;
     const uint64_t gid = (uint64_t)(a.id_base + (int64_t)wl * a.id_stride);
-    const int ox = a.origin[2 * frame], oy = a.origin[2 * frame + 1];
+    const double oxd = (double)a.origin[2 * frame], oyd = (double)a.origin[2 * frame + 1];
     double* st = a.state + (size_t)wl * (P + 1);
 
-    // lane j < P owns parameter j and its counters; lane P owns chi-square
+    // lane j < P owns parameter j; lane P holds chi-square
     double p = (lane <= P) ? st[lane] : 0.0;
     double chi_c = shfl_f64(p, P);
-    uint32_t tr = 0, ac = 0;
-    double sh = 0.0, m1 = 0.0, m2 = 0.0;
-    if (lane < P) {
-        tr = a.tries[(size_t)wl * P + lane];
-        ac = a.accepts[(size_t)wl * P + lane];
-    }
-    if (lane <= P) {
-        sh = a.shift[(size_t)wl * (P + 1) + lane];
-        m1 = a.moments[((size_t)wl * (P + 1) + lane) * 2];
-        m2 = a.moments[((size_t)wl * (P + 1) + lane) * 2 + 1];
-    }
 
     Coef<NB> cf;
-    if (lane < P) tv[lane] = p;
-    __syncwarp();
-    set_shape<NB>(cf, 0, (float)tv[L::I_SX], (float)tv[L::I_SY], (float)tv[L::I_TH]);
-    set_shape<NB>(cf, 1, (float)tv[L::I_SX2], (float)tv[L::I_SY2], (float)tv[L::I_TH2]);
-    float csa[2] = {cf.sa[0], cf.sa[1]}, csb[2] = {cf.sb[0], cf.sb[1]}, csc[2] = {cf.sc[0], cf.sc[1]};
+    stage_trial<NB>(ws.tf, lane, p, oxd, oyd);
+    load_shape<NB>(cf, 0, ws.tf);
+    load_shape<NB>(cf, 1, ws.tf);
+    if (lane == 0) {
+        ws.shape[0] = cf.sa[0]; ws.shape[1] = cf.sb[0]; ws.shape[2] = cf.sc[0];
+        ws.shape[4] = cf.sa[1]; ws.shape[5] = cf.sb[1]; ws.shape[6] = cf.sc[1];
+    }
 
-    int my_k = 0;
-    double my_step = 0.0, my_lnu = 0.0;
     int64_t next_rec = a.next_record;
     int64_t row = 0;
 
@@ -259,79 +267,78 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         if (slot == 0) {
             // lane l prepares the draws of update t0+u+l: 32 updates of random numbers at once
             const Draw dr = make_draw(a.seed, gid, (uint64_t)(a.t0 + u + lane), P);
-            my_k = dr.k;
             const double wz = a.widths[dr.k] * dr.z;
-            my_step = ((a.log_mask >> dr.k) & 1u) ? exp10(wz) : wz;
-            my_lnu = dr.lnu;
+            __syncwarp();
+            ws.k[lane] = dr.k;
+            ws.step[lane] = ((a.log_mask >> dr.k) & 1u) ? exp10(wz) : wz;
+            ws.lnu[lane] = dr.lnu;
+            __syncwarp();
         }
-        const int k = __shfl_sync(kFull, my_k, slot);                 // apf_step2.py:302
-        const double step = shfl_f64(my_step, slot);
-        const double lnu = shfl_f64(my_lnu, slot);
+        const int k = ws.k[slot];                                     // apf_step2.py:302
+        const double step = ws.step[slot];
         const double pk = shfl_f64(p, k);
         // proposal (apf_step2.py:63-70): additive, or multiplicative 10^(w z) for the log10
         // parameters; log10 of a negative value is nan there, and 0 stays 0.
         const double nv = ((a.log_mask >> k) & 1u) ? (pk < 0.0 ? nan("") : pk * step) : pk + step;
 
-        __syncwarp();
-        if (lane < P) tv[lane] = (lane == k) ? nv : p;                // :312-313
-        __syncwarp();
-        set_centres_amps<NB>(cf, tv, ox, oy, a.floor_index);
-        cf.sa[0] = csa[0]; cf.sb[0] = csb[0]; cf.sc[0] = csc[0];
-        cf.sa[1] = csa[1]; cf.sb[1] = csb[1]; cf.sc[1] = csc[1];
-        if (k >= L::I_SX) {                                           // a shape parameter moved
-            if (k == L::I_SX2 || k == L::I_SY2 || k == L::I_TH2)
-                set_shape<NB>(cf, 1, (float)tv[L::I_SX2], (float)tv[L::I_SY2], (float)tv[L::I_TH2]);
-            else
-                set_shape<NB>(cf, 0, (float)tv[L::I_SX], (float)tv[L::I_SY], (float)tv[L::I_TH]);
+        stage_trial<NB>(ws.tf, lane, (lane == k) ? nv : p, oxd, oyd);  // :312-313
+        load_centres_amps<NB>(cf, ws.tf, a.floor_index);
+        {
+            const float4 s0 = *reinterpret_cast<const float4*>(&ws.shape[0]);
+            const float4 s1 = *reinterpret_cast<const float4*>(&ws.shape[4]);
+            cf.sa[0] = s0.x; cf.sb[0] = s0.y; cf.sc[0] = s0.z;
+            cf.sa[1] = s1.x; cf.sb[1] = s1.y; cf.sc[1] = s1.z;
         }
-        const double chi_t = warp_chi2<NB, NX, NY, false>(cf, sd, sw, nullptr, lane);   // :314-316
+        const bool shape_moved = k >= L::I_SX;
+        const int which = (k == L::I_SX2 || k == L::I_SY2 || k == L::I_TH2) ? 1 : 0;
+        if (shape_moved) load_shape<NB>(cf, which, ws.tf);
+        build_row_table<NB, NY>(rt, cf, lane);
+        const double chi_t = warp_chi2<NB, NX, NY, false, true>(cf, rt, sd, sw, nullptr, lane);   // :314-316
 
         // accept iff u < exp(-(chi_t - chi_c)/2) (apf_step2.py:139-148); false on nan
-        const bool acc = lnu < -0.5 * (chi_t - chi_c);
-        if (lane == k) {
-            ++tr;                                                     // :304
-            if (acc) { ++ac; p = nv; }                                // :323-325
+        const bool acc = ws.lnu[slot] < -0.5 * (chi_t - chi_c);
+        if (lane == 0) {
+            atomicAdd(&a.tries[(size_t)wl * P + k], 1u);              // :304
+            if (acc) atomicAdd(&a.accepts[(size_t)wl * P + k], 1u);   // :323
         }
         if (acc) {
+            if (lane == k) p = nv;                                    // :325
             chi_c = chi_t;                                            // :327
-            csa[0] = cf.sa[0]; csb[0] = cf.sb[0]; csc[0] = cf.sc[0];
-            csa[1] = cf.sa[1]; csb[1] = cf.sb[1]; csc[1] = cf.sc[1];
+            if (shape_moved && lane == 0) {
+                ws.shape[4 * which + 0] = cf.sa[which];
+                ws.shape[4 * which + 1] = cf.sb[which];
+                ws.shape[4 * which + 2] = cf.sc[which];
+            }
         }
         if (a.t0 + u + 1 == next_rec) {                               // :342-351
             if (lane <= P) {
+                const size_t mi = (size_t)wl * (P + 1) + lane;
                 const double v = (lane == P) ? chi_c : p;
                 if (a.chain) a.chain[((size_t)row * a.n_walkers + wl) * (P + 1) + lane] = v;
-                const double dl = v - sh;
-                m1 += dl;
-                m2 = fma(dl, dl, m2);
+                const double dl = v - a.shift[mi];
+                atomicAdd(&a.moments[2 * mi], dl);                    // single writer: plain RED, in order
+                atomicAdd(&a.moments[2 * mi + 1], dl * dl);
             }
             ++row;
             next_rec += a.thin;
         }
     }
 
-    if (lane < P) {
-        st[lane] = p;
-        a.tries[(size_t)wl * P + lane] = tr;
-        a.accepts[(size_t)wl * P + lane] = ac;
-    }
+    if (lane < P) st[lane] = p;
     if (lane == P) st[P] = chi_c;
-    if (lane <= P) {
-        a.moments[((size_t)wl * (P + 1) + lane) * 2] = m1;
-        a.moments[((size_t)wl * (P + 1) + lane) * 2 + 1] = m2;
-    }
 }
 
 template <int NB, int NX, int NY, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_constant__ RunArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ WarpScratch scratch[NW];
+    __shared__ uint64_t bar;
     float* sd = reinterpret_cast<float*>(smem_raw);
     float* sw = sd + NX * NY;
-    double* trial = reinterpret_cast<double*>(sw + NX * NY);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(trial + NW * kTrialStride);
+    float* rt = sw + NX * NY;                       // [NW][NY][4*NB] row tables
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (threadIdx.x == 0) mbar_init(bar, 1);
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
 
     // contiguous share of the item list: consecutive items mostly share a frame
@@ -346,16 +353,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
             if (threadIdx.x == 0) {
                 constexpr uint32_t kBytes = NX * NY * sizeof(float);
                 fence_proxy_async();
-                mbar_expect_tx(bar, 2 * kBytes);
-                tma_bulk_g2s(sd, a.data + (size_t)f * NX * NY, kBytes, bar);
-                tma_bulk_g2s(sw, a.weight + (size_t)f * NX * NY, kBytes, bar);
+                mbar_expect_tx(&bar, 2 * kBytes);
+                tma_bulk_g2s(sd, a.data + (size_t)f * NX * NY, kBytes, &bar);
+                tma_bulk_g2s(sw, a.weight + (size_t)f * NX * NY, kBytes, &bar);
             }
-            mbar_wait(bar, phase);
+            mbar_wait(&bar, phase);
             phase ^= 1u;
             cur_frame = f;
+            prep_stamp(sd, sw, NX * NY);            // (d, w) -> (d*sqrt(w), -sqrt(w)), once per staged frame
+            __syncthreads();
         }
         if (warp < a.item_count[it])
-            run_walker<NB, NX, NY>(a, sd, sw, trial + warp * kTrialStride,
+            run_walker<NB, NX, NY>(a, sd, sw, scratch[warp], rt + warp * (NY * 4 * NB),
                                    a.walker_of[a.item_first[it] + warp], f, lane);
     }
 }
@@ -539,8 +548,9 @@ static int check_problem(const lapf_problem* p) {
     if (p->ny <= 0 || p->nx <= 0 || p->n_frames <= 0)
         return fail(LAPF_ERR_INVALID, "bad shape ny=%d nx=%d n_frames=%d", p->ny, p->nx, p->n_frames);
     const int P = 3 * p->nbody + 10;
-    if (p->floor_index < 0 || p->floor_index >= P)
-        return fail(LAPF_ERR_INVALID, "floor_index %d outside [0,%d)", p->floor_index, P);
+    if (p->floor_index < 2 * p->nbody || p->floor_index >= P)
+        return fail(LAPF_ERR_INVALID, "floor_index %d outside [%d,%d) (positions cannot be the floor)",
+                    p->floor_index, 2 * p->nbody, P);
     if (!p->data || !p->weight || !p->origin) return fail(LAPF_ERR_INVALID, "data/weight/origin must be device pointers");
     if (((uintptr_t)p->data & 15) || ((uintptr_t)p->weight & 15))
         return fail(LAPF_ERR_INVALID, "data and weight must be 16-byte aligned (TMA bulk copies)");
@@ -656,7 +666,7 @@ static int configure_gibbs(lapf_sampler* s) {
     auto kern = gibbs_kernel<NB, NX, NX, NW, MINB>;
     s->nw = NW;
     s->minb = MINB;
-    s->smem = 2 * sizeof(float) * NX * NX + sizeof(double) * NW * kTrialStride + 16;
+    s->smem = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * NX * 4 * NB;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, s->smem));
@@ -677,12 +687,12 @@ static int launch_gibbs(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
 #define LAPF_DISPATCH_GIBBS(FN, ...)                                                        \
     do {                                                                                    \
         const int nb__ = s->cfg.problem.nbody, nx__ = s->cfg.problem.nx;                    \
-        if (nb__ == 2 && nx__ == 32) return FN<2, 32, 8, 2>(__VA_ARGS__);                   \
-        if (nb__ == 2 && nx__ == 64) return FN<2, 64, 8, 2>(__VA_ARGS__);                   \
+        if (nb__ == 2 && nx__ == 32) return FN<2, 32, 16, 1>(__VA_ARGS__);                   \
+        if (nb__ == 2 && nx__ == 64) return FN<2, 64, 16, 1>(__VA_ARGS__);                   \
         if (nb__ == 2 && nx__ == 128) return FN<2, 128, 16, 1>(__VA_ARGS__);                \
-        if (nb__ == 3 && nx__ == 32) return FN<3, 32, 8, 2>(__VA_ARGS__);                   \
-        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 8, 2>(__VA_ARGS__);                   \
-        if (nb__ == 3 && nx__ == 128) return FN<3, 128, 16, 1>(__VA_ARGS__);                \
+        if (nb__ == 3 && nx__ == 32) return FN<3, 32, 16, 1>(__VA_ARGS__);                   \
+        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 16, 1>(__VA_ARGS__);                   \
+        if (nb__ == 3 && nx__ == 128) return FN<3, 128, 12, 1>(__VA_ARGS__);                \
         return fail(LAPF_ERR_INVALID, "unsupported sampler shape nbody=%d nx=%d", nb__, nx__); \
     } while (0)
 

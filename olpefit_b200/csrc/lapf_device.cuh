@@ -7,7 +7,7 @@
 //   philox / draws  counter-based random stream (replaces numpy's global MT, apf_step2.py:64,68,143,302)
 //
 // Numerics: pixel terms in FP32 with stamp-local coordinates, ex2.approx
-// with coefficients pre-scaled by -log2(e); per-row FP32 partial sums are folded into an FP64
+// with coefficients pre-scaled by -log2(e); FP32 partial sums of a few rows are folded into an FP64
 // accumulator; everything that crosses lanes, the stored chi-square and the Metropolis
 // difference are FP64.  The pixel->lane map and the reduction tree are fixed, so chi-square is
 // a pure function of the parameter vector.
@@ -121,35 +121,53 @@ __device__ __forceinline__ void set_shape(Coef<NB>& cf, int which, float sx, flo
     cf.sc[which] = -0.5f * kLog2e * (s * s * ivx + c * c * ivy);
 }
 
-// Centres (stamp-local) and amplitudes from a parameter vector in frame coordinates
-// (build_2d_gaussian, apf_step2.py:95-101).  `pv` may point to shared or global memory.
+// Per-warp staging of one (trial) parameter vector as FP32 in shared memory.  Lane j < P holds
+// parameter j in FP64 frame coordinates; positions are converted to stamp-local coordinates in
+// FP64 before rounding to FP32.  Layout of tf[]:
+//   tf[j], j < P            parameter j (positions: local)
+//   tf[P + j], j < 2*NB     centre coordinate j of the WIDE component: position j + dx or dy
+// Every conversion is done once, by the owning lane; afterwards all lanes read tf[] as broadcasts.
 template <int NB>
-__device__ __forceinline__ void set_centres_amps(Coef<NB>& cf, const double* pv, int ox, int oy,
-                                                 int floor_index) {
+__device__ __forceinline__ void stage_trial(float* tf, int lane, double mine, double oxd, double oyd) {
     using L = Layout<NB>;
-    const double dx = pv[L::I_DX], dy = pv[L::I_DY];
-    const float ratio = (float)pv[L::I_RATIO], bkgd = (float)pv[L::I_BKGD];
+    const double dxv = shfl_f64(mine, L::I_DX), dyv = shfl_f64(mine, L::I_DY);
+    __syncwarp();   // readers of the previous vector are done
+    if (lane < 2 * NB) {
+        const double base = mine - ((lane & 1) ? oyd : oxd);
+        tf[lane] = (float)base;
+        tf[L::P + lane] = (float)(base + ((lane & 1) ? dyv : dxv));
+    } else if (lane < L::P) {
+        tf[lane] = (float)mine;
+    }
+    __syncwarp();
+}
+
+// Centres and amplitudes from the staged vector (build_2d_gaussian, apf_step2.py:95-101).
+template <int NB>
+__device__ __forceinline__ void load_centres_amps(Coef<NB>& cf, const float* tf, int floor_index) {
+    using L = Layout<NB>;
+    const float ratio = tf[L::I_RATIO], bkgd = tf[L::I_BKGD];
 #pragma unroll
     for (int o = 0; o < NB; ++o) {
-        const double xc = pv[2 * o] - (double)ox, yc = pv[2 * o + 1] - (double)oy;
-        cf.x0[2 * o] = (float)xc;
-        cf.y0[2 * o] = (float)yc;
-        cf.x0[2 * o + 1] = (float)(xc + dx);
-        cf.y0[2 * o + 1] = (float)(yc + dy);
-        const float a = (float)pv[L::I_AMP + o] - bkgd;   // :95
+        cf.x0[2 * o] = tf[2 * o];
+        cf.y0[2 * o] = tf[2 * o + 1];
+        cf.x0[2 * o + 1] = tf[L::P + 2 * o];
+        cf.y0[2 * o + 1] = tf[L::P + 2 * o + 1];
+        const float a = tf[L::I_AMP + o] - bkgd;          // :95
         const float aw = a * ratio;                       // :96
         cf.amp[2 * o] = a - aw;                           // :97
         cf.amp[2 * o + 1] = aw;
     }
-    cf.floor = (float)pv[floor_index];                    // apf_step2.py:119-120
+    cf.floor = tf[floor_index];                           // apf_step2.py:119-120
 }
 
 template <int NB>
-__device__ __forceinline__ void set_all(Coef<NB>& cf, const double* pv, int ox, int oy, int floor_index) {
+__device__ __forceinline__ void load_shape(Coef<NB>& cf, int which, const float* tf) {
     using L = Layout<NB>;
-    set_centres_amps<NB>(cf, pv, ox, oy, floor_index);
-    set_shape<NB>(cf, 0, (float)pv[L::I_SX], (float)pv[L::I_SY], (float)pv[L::I_TH]);
-    set_shape<NB>(cf, 1, (float)pv[L::I_SX2], (float)pv[L::I_SY2], (float)pv[L::I_TH2]);
+    if (which)
+        set_shape<NB>(cf, 1, tf[L::I_SX2], tf[L::I_SY2], tf[L::I_TH2]);
+    else
+        set_shape<NB>(cf, 0, tf[L::I_SX], tf[L::I_SY], tf[L::I_TH]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -174,12 +192,49 @@ struct Geo {
     static_assert(NX % PW == 0 && (NX == 32 || NX % 64 == 0), "unsupported stamp width");
 };
 
-template <int NB, int NX, int NY, bool STORE>
-__device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __restrict__ d,
-                                            const float* __restrict__ w, float* __restrict__ model_out,
-                                            int lane) {
+// Row table: the row-dependent part of every exponent, computed ONCE per proposal by the warp
+// (row r by lane r mod 32) instead of once per row step by every lane:
+//   rt[r][k]     = sb_k * dy        rt[r][K + k] = sc_k * dy^2,      dy = r - y0_k
+// so that per pixel and component  q = fma(dx, fma(sa_k, dx, rt[r][k]), rt[r][K+k]).
+// The four row groups of a warp read four consecutive rows: one conflict-free wavefront per load.
+template <int NB, int NY>
+__device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Coef<NB>& cf, int lane) {
+    constexpr int K = 2 * NB;
+    static_assert(NY % 32 == 0, "row table is built 32 rows at a time");
+    __syncwarp();   // readers of the previous table are done
+#pragma unroll
+    for (int r0 = 0; r0 < NY; r0 += 32) {
+        const float fr = (float)(r0 + lane);
+        float v[2 * K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float yd = fr - cf.y0[k];
+            v[k] = cf.sb[k & 1] * yd;
+            v[K + k] = (cf.sc[k & 1] * yd) * yd;
+        }
+        float4* o = reinterpret_cast<float4*>(rt + (r0 + lane) * 2 * K);
+#pragma unroll
+        for (int q = 0; q < 2 * K / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    __syncwarp();
+}
+
+// PREP = true: the planes already hold  d*sqrt(w)  and  -sqrt(w)  (the sampler converts a stamp
+// once after staging it); PREP = false: raw data / weight planes, converted per pixel.  Both give
+// bit-identical chi-square: the residual is always  r = fma(-sqrt(w), m, d*sqrt(w)),  chi2 += r*r.
+//
+// Arithmetic is issued as packed FFMA2 (fma.rn.f32x2, new on sm_100): two adjacent pixels per
+// instruction, scalar coefficients as broadcast operands.  Per pixel PAIR and component that is
+// 3 FFMA2 + 2 MUFU.EX2, which keeps the issue slots needed per MUFU below the SFU's own rate
+// (measured: a MUFU costs ~4 issue cycles), so the loop is SFU-bound.
+template <int NB, int NX, int NY, bool STORE, bool PREP>
+__device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __restrict__ rt,
+                                            const float* __restrict__ d, const float* __restrict__ w,
+                                            float* __restrict__ model_out, int lane) {
     using G = Geo<NX>;
     constexpr int K = 2 * NB;
+    constexpr int STEPS = NY / G::RG;            // row steps per panel
+    constexpr int FOLD = STEPS % 4 == 0 ? 4 : 1; // FP32 partials are folded into FP64 every FOLD steps
     static_assert(NY % G::RG == 0, "unsupported stamp height");
     const int c = lane % G::LPR, g = lane / G::LPR;
     const int swap = (G::PW == 32) ? (g & 1) : 0;
@@ -188,59 +243,92 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
     for (int pan = 0; pan < G::PANELS; ++pan) {
         const int colA = pan * G::PW + 4 * c + (G::PW / 2) * swap;
         const int colB = pan * G::PW + 4 * c + (G::PW / 2) * (1 - swap);
-        float xd[K][8];
+        float2 xd[K][4];   // pixel pairs: (0,1) (2,3) of group A, (0,1) (2,3) of group B
 #pragma unroll
         for (int k = 0; k < K; ++k) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                xd[k][j] = (float)(colA + j) - cf.x0[k];
-                xd[k][4 + j] = (float)(colB + j) - cf.x0[k];
+            for (int jj = 0; jj < 2; ++jj) {
+                xd[k][jj] = make_float2((float)(colA + 2 * jj) - cf.x0[k], (float)(colA + 2 * jj + 1) - cf.x0[k]);
+                xd[k][2 + jj] = make_float2((float)(colB + 2 * jj) - cf.x0[k], (float)(colB + 2 * jj + 1) - cf.x0[k]);
             }
         }
+        const float* rp = rt + g * 2 * K;
+        const float* dp = d + g * NX;
+        const float* wp = w + g * NX;
+        float* mp = STORE ? model_out + g * NX : nullptr;
 #pragma unroll 1
-        for (int i = 0; i < NY / G::RG; ++i) {
-            const int r = i * G::RG + g;
-            const float fr = (float)r;
-            float by[K], cy[K];
+        for (int ib = 0; ib < STEPS; ib += FOLD) {
+            float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll 1
+            for (int ii = 0; ii < FOLD; ++ii) {
+                float rc[2 * K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const float yd = fr - cf.y0[k];
-                by[k] = cf.sb[k & 1] * yd;
-                cy[k] = (cf.sc[k & 1] * yd) * yd;
-            }
-            const float4 dA = *reinterpret_cast<const float4*>(d + r * NX + colA);
-            const float4 dB = *reinterpret_cast<const float4*>(d + r * NX + colB);
-            const float4 wA = *reinterpret_cast<const float4*>(w + r * NX + colA);
-            const float4 wB = *reinterpret_cast<const float4*>(w + r * NX + colB);
-            float m[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) m[j] = cf.floor;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float t = fmaf(cf.sa[k & 1], xd[k][j], by[k]);
-                    const float q = fmaf(xd[k][j], t, cy[k]);
-                    m[j] = fmaf(cf.amp[k], ex2_approx(q), m[j]);
+                for (int q = 0; q < 2 * K / 4; ++q) {
+                    const float4 t4 = reinterpret_cast<const float4*>(rp)[q];
+                    rc[4 * q] = t4.x; rc[4 * q + 1] = t4.y; rc[4 * q + 2] = t4.z; rc[4 * q + 3] = t4.w;
                 }
-            }
-            if (STORE) {
-                *reinterpret_cast<float4*>(model_out + r * NX + colA) = make_float4(m[0], m[1], m[2], m[3]);
-                *reinterpret_cast<float4*>(model_out + r * NX + colB) = make_float4(m[4], m[5], m[6], m[7]);
-            }
-            const float dv[8] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w};
-            const float wv[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
-            float s0 = 0.f, s1 = 0.f;
+                const float4 dA = *reinterpret_cast<const float4*>(dp + colA);
+                const float4 dB = *reinterpret_cast<const float4*>(dp + colB);
+                const float4 wA = *reinterpret_cast<const float4*>(wp + colA);
+                const float4 wB = *reinterpret_cast<const float4*>(wp + colB);
+                float2 m[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float r0 = dv[j] - m[j], r1 = dv[4 + j] - m[4 + j];
-                s0 = fmaf(wv[j] * r0, r0, s0);
-                s1 = fmaf(wv[4 + j] * r1, r1, s1);
+                for (int j = 0; j < 4; ++j) m[j] = make_float2(cf.floor, cf.floor);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float2 sa2 = make_float2(cf.sa[k & 1], cf.sa[k & 1]);
+                    const float2 by2 = make_float2(rc[k], rc[k]);
+                    const float2 cy2 = make_float2(rc[K + k], rc[K + k]);
+                    const float2 am2 = make_float2(cf.amp[k], cf.amp[k]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 t = __ffma2_rn(sa2, xd[k][j], by2);
+                        const float2 q = __ffma2_rn(xd[k][j], t, cy2);
+                        const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
+                        m[j] = __ffma2_rn(am2, e, m[j]);
+                    }
+                }
+                if (STORE) {
+                    *reinterpret_cast<float4*>(mp + colA) = make_float4(m[0].x, m[0].y, m[1].x, m[1].y);
+                    *reinterpret_cast<float4*>(mp + colB) = make_float4(m[2].x, m[2].y, m[3].x, m[3].y);
+                    mp += G::RG * NX;
+                }
+                float2 dv[4] = {make_float2(dA.x, dA.y), make_float2(dA.z, dA.w), make_float2(dB.x, dB.y),
+                                make_float2(dB.z, dB.w)};
+                float2 wv[4] = {make_float2(wA.x, wA.y), make_float2(wA.z, wA.w), make_float2(wB.x, wB.y),
+                                make_float2(wB.z, wB.w)};
+                if (!PREP) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float rx = sqrtf(wv[j].x), ry = sqrtf(wv[j].y);
+                        dv[j] = make_float2(dv[j].x * rx, dv[j].y * ry);
+                        wv[j] = make_float2(-rx, -ry);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float2 r0 = __ffma2_rn(wv[j], m[j], dv[j]);
+                    const float2 r1 = __ffma2_rn(wv[2 + j], m[2 + j], dv[2 + j]);
+                    s0 = __ffma2_rn(r0, r0, s0);
+                    s1 = __ffma2_rn(r1, r1, s1);
+                }
+                rp += G::RG * 2 * K;
+                dp += G::RG * NX;
+                wp += G::RG * NX;
             }
-            acc += (double)(s0 + s1);
+            acc += (double)((s0.x + s0.y) + (s1.x + s1.y));
         }
     }
     return warp_sum_f64(acc);
+}
+
+// In-place conversion of a staged stamp to (d*sqrt(w), -sqrt(w)); called by the whole CTA.
+__device__ __forceinline__ void prep_stamp(float* __restrict__ sd, float* __restrict__ sw, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float r = sqrtf(sw[i]);
+        sw[i] = -r;
+        sd[i] *= r;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -268,6 +356,17 @@ struct Draw {
     int k;        // parameter index
     double z;     // standard normal
     double lnu;   // log of the uniform (-inf when the uniform is 0)
+};
+
+// Per-warp sampler scratch in shared memory: the staged trial vector, the random numbers of the
+// next 32 updates (one update per lane, read back as broadcasts) and the shapes of the current
+// state.  Keeping these out of registers leaves the register file to the pixel loop.
+struct WarpScratch {
+    float tf[32];        // staged trial vector (stage_trial)
+    double step[32];     // proposal step of update slot i: w*z, or 10^(w*z) for log10 parameters
+    double lnu[32];      // log of the accept/reject uniform of update slot i
+    int k[32];           // parameter index of update slot i
+    float shape[8];      // sa0 sb0 sc0 - sa1 sb1 sc1 -  of the CURRENT state
 };
 
 __device__ __forceinline__ Draw make_draw(uint64_t seed, uint64_t walker_id, uint64_t t, int nparam) {

@@ -1,0 +1,149 @@
+// Development micro-benchmarks for the SFU/FP32 mix (not part of the product).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu && tools/microbench
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ float ex2a(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// NF independent FFMAs per EX2, 8 EX2 chains per thread
+template <int NF>
+__global__ void __launch_bounds__(256) mix_kernel(float* out, int iters, float a, float b) {
+    float x[8], y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x[j] = 0.1f * (threadIdx.x & 7) + 0.05f * j; y[j] = x[j] + 1.f; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            x[j] = ex2a(-x[j]);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) y[(j + f) & 7] = fmaf(y[(j + f) & 7], a, b);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += x[j] + y[j];
+    if (s == 123.456f) out[0] = s;
+}
+
+// the real dependency pattern: 4 components x 8 pixels per step, coefficients in registers
+__global__ void __launch_bounds__(256) pattern_kernel(float* out, int iters, float a, float b) {
+    float xd[4][8], m[8];
+    float sa[2] = {-0.15f * a, -0.02f * a}, amp[4] = {100.f, 20.f, 3.f, 1.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xd[k][j] = (float)((threadIdx.x & 7) * 8 + j) - 3.3f * k * b;
+    float s = 0.f, fr = (float)(threadIdx.x >> 3);
+    for (int i = 0; i < iters; ++i) {
+        float by[4], cy[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { float yd = fr - 2.2f * k; by[k] = 0.01f * b * yd; cy[k] = (sa[k & 1] * yd) * yd; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = 6.4f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float t = fmaf(sa[k & 1], xd[k][j], by[k]);
+                float q = fmaf(xd[k][j], t, cy[k]);
+                m[j] = fmaf(amp[k], ex2a(q), m[j]);
+            }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { float r = 7.f - m[j]; s = fmaf(0.5f * r, r, s); }
+        fr += 4.f; if (fr > 60.f) fr -= 64.f;
+    }
+    if (s == 123.456f) out[0] = s;
+}
+
+// NF2 independent packed FFMA2 per pair of EX2
+template <int NF2>
+__global__ void __launch_bounds__(256) mix2_kernel(float* out, int iters, float a, float b) {
+    float x[8]; float2 y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x[j] = 0.1f * (threadIdx.x & 7) + 0.05f * j; y[j] = make_float2(x[j] + 1.f, x[j] + 2.f); }
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            x[j] = ex2a(-x[j]);
+            x[j + 1] = ex2a(-x[j + 1]);
+#pragma unroll
+            for (int f = 0; f < NF2; ++f) y[(j + f) & 7] = __ffma2_rn(y[(j + f) & 7], a2, b2);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += x[j] + y[j].x + y[j].y;
+    if (s == 123.456f) out[0] = s;
+}
+
+// the real dependency pattern with pixel pairs and FFMA2
+__global__ void __launch_bounds__(256) pattern2_kernel(float* out, int iters, float a, float b) {
+    float2 xd[4][4], m[4];
+    float2 sa[2] = {make_float2(-0.15f * a, -0.15f * a), make_float2(-0.02f * a, -0.02f * a)};
+    float2 amp[4] = {make_float2(100.f, 100.f), make_float2(20.f, 20.f), make_float2(3.f, 3.f), make_float2(1.f, 1.f)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float v = (float)((threadIdx.x & 7) * 8 + 2 * j) - 3.3f * k * b; xd[k][j] = make_float2(v, v + 1.f); }
+    float2 s = make_float2(0.f, 0.f); float fr = (float)(threadIdx.x >> 3);
+    for (int i = 0; i < iters; ++i) {
+        float2 by[4], cy[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { float yd = fr - 2.2f * k; float bb = 0.01f * b * yd, cc = (sa[k & 1].x * yd) * yd; by[k] = make_float2(bb, bb); cy[k] = make_float2(cc, cc); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = make_float2(6.4f, 6.4f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 t = __ffma2_rn(sa[k & 1], xd[k][j], by[k]);
+                float2 q = __ffma2_rn(xd[k][j], t, cy[k]);
+                float2 e = make_float2(ex2a(q.x), ex2a(q.y));
+                m[j] = __ffma2_rn(amp[k], e, m[j]);
+            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 r = __ffma2_rn(make_float2(-0.5f, -0.5f), m[j], make_float2(7.f, 7.f)); s = __ffma2_rn(r, r, s); }
+        fr += 4.f; if (fr > 60.f) fr -= 64.f;
+    }
+    if (s.x + s.y == 123.456f) out[0] = s.x;
+}
+
+template <typename F>
+double time_it(F launch, double ops) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0; float ms;
+    for (int r = 0; r < 4; ++r) {
+        cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r) best = best > ops / (ms * 1e-3) ? best : ops / (ms * 1e-3);
+    }
+    return best;
+}
+
+int main() {
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    float* d; cudaMalloc(&d, 64);
+    const int iters = 4096;
+    const double nominal = sms * 16.0 * 1.965e9;
+    printf("SMs %d, nominal EX2 peak at 1965 MHz: %.1f Gex2/s\n", sms, nominal / 1e9);
+    for (int wps : {8, 16, 32, 64}) {          // resident warps per SM (blocks of 8 warps)
+        int blocks = sms * (wps / 8);
+        double ops = (double)blocks * 256 * iters * 8.0;
+        printf("warps/SM %2d:", wps);
+        printf("  ex2+0f %.0f", time_it([&] { mix_kernel<0><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
+        printf("  +2f %.0f", time_it([&] { mix_kernel<2><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
+        printf("  +4f %.0f", time_it([&] { mix_kernel<4><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
+        printf("  +5f %.0f", time_it([&] { mix_kernel<5><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
+        printf("  +6f %.0f", time_it([&] { mix_kernel<6><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
+        printf("  +7f %.0f", time_it([&] { mix_kernel<7><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
+        double pops = (double)blocks * 256 * iters * 32.0;
+        printf("  | ffma2 per 2 ex2: 2:%.0f", time_it([&] { mix2_kernel<2><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
+        printf(" 4:%.0f", time_it([&] { mix2_kernel<4><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
+        printf(" 6:%.0f", time_it([&] { mix2_kernel<6><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
+        printf(" 8:%.0f", time_it([&] { mix2_kernel<8><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
+        printf("  pattern2 %.0f", time_it([&] { pattern2_kernel<<<blocks, 256>>>(d, iters, .999f, .001f); }, pops) / 1e9);
+        printf("  pattern %.0f Gex2/s\n", time_it([&] { pattern_kernel<<<blocks, 256>>>(d, iters, .999f, .001f); }, pops) / 1e9);
+    }
+    return 0;
+}
