@@ -304,10 +304,9 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         if (acc) {
             if (lane == k) p = nv;                                    // :325
             chi_c = chi_t;                                            // :327
-            if (shape_moved && lane == 0) {
-                ws.shape[4 * which + 0] = cf.sa[which];
-                ws.shape[4 * which + 1] = cf.sb[which];
-                ws.shape[4 * which + 2] = cf.sc[which];
+            if (shape_moved && lane == 0) {   // constant indices only: keeps cf in registers
+                if (which) { ws.shape[4] = cf.sa[1]; ws.shape[5] = cf.sb[1]; ws.shape[6] = cf.sc[1]; }
+                else       { ws.shape[0] = cf.sa[0]; ws.shape[1] = cf.sb[0]; ws.shape[2] = cf.sc[0]; }
             }
         }
         if (a.t0 + u + 1 == next_rec) {                               // :342-351

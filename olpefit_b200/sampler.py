@@ -125,3 +125,56 @@ class GibbsSampler:
                                                cnt.data_ptr(), _stream_ptr(dev)))
         return {"tries": tot[:pn], "accepts": tot[pn:2 * pn], "min_tries": tot[2 * pn],
                 "moments": mom, "walkers_per_frame": cnt[:nf], "rows": cnt[nf]}
+
+
+class ChainStreamer:
+    """Double-buffered chain output (K3): while the GPU computes segment i+1 into one device
+    buffer, segment i travels to pinned host memory on a copy stream and is handed to the caller.
+    Replaces the reference's in-memory hstack + whole-file rewrite (apf_step2.py:346-360).
+
+        streamer = ChainStreamer(sampler, max_updates_per_segment)
+        seg = streamer.run(n)      # launches n updates; returns the PREVIOUS segment (numpy) or None
+        seg = streamer.finish()    # the last segment
+    """
+
+    def __init__(self, sampler: GibbsSampler, max_updates: int):
+        self.s = sampler
+        dev = sampler.domain.device
+        cap_rows = max(1, -(-int(max_updates) // sampler.thin) + 1)
+        shape = (cap_rows, sampler.n_walkers, sampler.nparam + 1)
+        self.dev = [torch.empty(shape, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.host = [torch.empty(shape, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.pending = None          # (buffer index, rows)
+        self.i = 0
+        self.max_updates = int(max_updates)
+
+    def _collect(self):
+        if self.pending is None:
+            return None
+        j, rows = self.pending
+        self.pending = None
+        self.done[j].synchronize()
+        return self.host[j][:rows].numpy()
+
+    def run(self, n_updates: int):
+        if n_updates > self.max_updates:
+            raise ValueError("segment longer than the streamer was sized for")
+        s, i = self.s, self.i
+        compute = torch.cuda.current_stream(s.domain.device)
+        compute.wait_event(self.done[i])            # the copy out of dev[i] two segments ago is finished
+        chain = s.run(n_updates, out=self.dev[i])
+        rows = int(chain.shape[0])
+        if rows:
+            nbytes = rows * s.n_walkers * (s.nparam + 1) * 8
+            _lib.check(s.lib.lapf_chain_drain(self.dev[i].data_ptr(), self.host[i].data_ptr(), nbytes,
+                                              compute.cuda_stream, self.copy_stream.cuda_stream))
+        self.done[i].record(self.copy_stream)
+        prev = self._collect()                      # overlaps with the segment just launched
+        self.pending = (i, rows)
+        self.i = 1 - i
+        return prev
+
+    def finish(self):
+        return self._collect()

@@ -101,21 +101,20 @@ def make_stamps(n_frames, size, nbody=2, dtype=np.float32):
 
 
 def step1_guess(image, nbody=2, origin=(0, 0), sky_xy=None):
-    """A step-1 style initial guess (apf_step1.py:145-163): brightest pixel (+0.5) in a 21x21
-    box around each source, plus an empty-sky corner.  Coordinates are frame coordinates."""
+    """A step-1 style initial guess (apf_step1.py:145-163) in frame coordinates: the star at its
+    brightest pixel + 0.5 (the reference searches a 21x21 box around the click); a companion at the
+    pixel containing it + 0.5 (a faint companion sitting on the star's wing is not the brightest
+    pixel of any box, the user's click decides); plus an empty-sky corner for the background box."""
     ox, oy = origin
-    srcs = [STAR_XY, COMP_XY] + ([COMP2_XY] if nbody == 3 else [])
     work = np.array(image, dtype=np.float64)
     work[work > 0.8 * 22000.0] = -np.inf  # do not lock on to hot pixels
-    out = []
-    for (sx, sy) in srcs:
-        xm, ym = int(sx) - ox, int(sy) - oy
-        # the companion sits on the star's wing: search a tighter box for faint sources
-        half = 10 if (sx, sy) == STAR_XY else 3
-        ylo, xlo = max(ym - half, 0), max(xm - half, 0)
-        box = work[ylo:ym + half + 1, xlo:xm + half + 1]
-        iy, ix = np.unravel_index(np.argmax(box), box.shape)
-        out += [xlo + ix + 0.5 + ox, ylo + iy + 0.5 + oy]
+    xm, ym = int(STAR_XY[0]) - ox, int(STAR_XY[1]) - oy
+    ylo, xlo = max(ym - 10, 0), max(xm - 10, 0)
+    box = work[ylo:ym + 11, xlo:xm + 11]
+    iy, ix = np.unravel_index(np.argmax(box), box.shape)
+    out = [xlo + ix + 0.5 + ox, ylo + iy + 0.5 + oy]
+    for (sx, sy) in [COMP_XY] + ([COMP2_XY] if nbody == 3 else []):
+        out += [math.floor(sx) + 0.5, math.floor(sy) + 0.5]
     if sky_xy is None:
         sky_xy = (ox + 1, oy + 1)
     out += [float(int(sky_xy[0])), float(int(sky_xy[1]))]

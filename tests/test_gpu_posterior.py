@@ -1,0 +1,68 @@
+"""Statistical parity (BASELINE.json: posterior medians and 68% intervals of separation and
+position angle must match a reference CPU run within Monte-Carlo error on the same frame).
+
+The CPU side is tests/golden/posterior_2body_s32.npz, produced by tools/make_posterior_fixture.py:
+64 walkers of the float64 numpy oracle with numpy's Mersenne-Twister stream (the reference's
+stream), 50,000 updates each, first 10,000 dropped, every 10th kept.  The GPU side runs the same
+configuration with 2048 walkers on the Philox stream.  Bit-equal chains are impossible by design
+(the reference is unseeded); the comparison is distributional, with standard errors taken from
+the spread between the CPU walkers."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lapf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+HEADER = {"itime": 1.0, "coadds": 1, "multisam": 1, "sampmode": 2}
+QS = [15.865, 50.0, 84.135]
+
+
+def test_separation_and_position_angle_posterior_match_cpu_reference(golden_dir):
+    import torch
+    from olpefit_b200 import chains, frame, sampler, synth
+
+    z = np.load(os.path.join(golden_dir, "posterior_2body_s32.npz"))
+    size, nbody, epoch = int(z["size"]), int(z["nbody"]), int(z["epoch"])
+    ox, oy = (int(v) for v in z["origin"])
+    img, _ = synth.make_frame(epoch, nbody, region=(oy, oy + size, ox, ox + size))
+    dom = frame.prepare_domain(img, HEADER, origin=(ox, oy), nbody=nbody)
+    walkers = 2048
+    with sampler.GibbsSampler(dom, np.tile(z["p0"], (walkers, 1)), seed=20260101,
+                              burn_in=int(z["burn"]), thin=int(z["thin"])) as s:
+        chain = s.run(int(z["updates"]))
+        st = s.stats()
+        acc = (st["accepts"].double() / st["tries"].double()).cpu().numpy()
+    rows = chain.cpu().numpy()                                    # [rows, walkers, P+1]
+    n_cpu = int(z["walkers"])
+    assert rows.shape[0] == (int(z["updates"]) - int(z["burn"])) // int(z["thin"]) + 1
+
+    sep, pa = chains.separation_pa(rows[..., 0], rows[..., 1], rows[..., 2], rows[..., 3])
+    for name, vals, q_cpu, q_walker in (("sep", sep, z["sep_q"], z["sep_q_walker"]),
+                                        ("pa", pa, z["pa_q"], z["pa_q_walker"])):
+        q_gpu = np.percentile(vals, QS)
+        # Monte-Carlo standard error of each pooled CPU quantile from the spread between walkers;
+        # the same for the GPU walkers (32x more of them)
+        se_cpu = q_walker.std(axis=0, ddof=1) / np.sqrt(n_cpu)
+        se_gpu = np.percentile(vals, QS, axis=0).std(axis=1, ddof=1) / np.sqrt(walkers)
+        zscore = (q_gpu - q_cpu) / np.sqrt(se_cpu ** 2 + se_gpu ** 2)
+        print(name, "gpu", q_gpu, "cpu", q_cpu, "z", zscore)
+        assert np.all(np.abs(zscore) < 5.0), (name, q_gpu, q_cpu, zscore)
+        # and the 68% interval has the same width to a few per cent
+        assert (q_gpu[2] - q_gpu[0]) == pytest.approx(q_cpu[2] - q_cpu[0], rel=0.05)
+
+    # every sampled parameter (not only the astrometry): pooled mean within Monte-Carlo error
+    flat = rows.reshape(-1, rows.shape[-1])
+    mean_gpu = flat.mean(axis=0)
+    se_cpu = z["param_mean_walker"].std(axis=0, ddof=1) / np.sqrt(n_cpu)
+    se_gpu = rows.mean(axis=0).std(axis=0, ddof=1) / np.sqrt(walkers)
+    zscore = (mean_gpu - z["param_mean"]) / np.sqrt(se_cpu ** 2 + se_gpu ** 2)
+    print("parameter z-scores", np.round(zscore, 2))
+    assert np.all(np.abs(zscore) < 5.0), zscore
+    # acceptance rates with the reference jump widths agree too
+    np.testing.assert_allclose(acc, z["acceptance"], atol=0.02)
+    # truth is inside the posterior bulk (sanity of the whole chain: synthetic truth is in-model)
+    t_sep, t_pa = orc.separation_pa(*z["truth"][:4])
+    assert np.percentile(sep, 0.5) < t_sep < np.percentile(sep, 99.5)
+    assert np.percentile(pa, 0.5) < t_pa < np.percentile(pa, 99.5)
