@@ -6,7 +6,7 @@
 
 Workload (BASELINE.json configs[2], the single-GPU throughput configuration): 65,536 independent
 walkers per GPU spread over 100 synthetic NIRC2-like epochs, 64 x 64 stamps, 2-body model.
-One "step" = ``--updates-per-step`` Gibbs updates of every walker (default 64 = 4 sweeps of the
+One "step" = ``--updates-per-step`` Gibbs updates of every walker (default 128 = 8 sweeps of the
 16 parameters), recording one chain row per sweep.  Metric: pixel-model evaluations per second
 (= Gibbs updates/s x pixels per stamp); Gibbs updates/s is reported next to it.
 """
@@ -35,17 +35,19 @@ UNIT = "pixel-evals/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--walkers", type=int, default=65536, help="walkers per GPU")
     ap.add_argument("--frames", type=int, default=100)
     ap.add_argument("--stamp", type=int, default=64, choices=[32, 64, 128])
     ap.add_argument("--nbody", type=int, default=2, choices=[2, 3])
-    ap.add_argument("--updates-per-step", type=int, default=64)
+    ap.add_argument("--updates-per-step", type=int, default=128)
     ap.add_argument("--thin", type=int, default=16)
     ap.add_argument("--seed", type=int, default=2019)
-    ap.add_argument("--cpu-updates", type=int, default=12000, help="updates per CPU walker in the baseline sample")
+    ap.add_argument("--team", type=int, default=1, choices=[1, 4, 16], help="warps per walker (16 for few walkers)")
+    ap.add_argument("--cpu-updates", type=int, default=80000, help="updates per CPU walker in the baseline sample")
+    ap.add_argument("--ref-updates-per-step", type=int, default=4000, help="updates per CPU walker and step, --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -98,7 +100,7 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(1, a.cpu_updates // 4)
+    per_step = max(1, a.ref_updates_per_step)
     times = []
     for i in range(a.warmup + a.steps):
         t, n, _ = cpu_walkers(a.nbody, a.stamp, per_step, cores)
@@ -219,7 +221,7 @@ def run_b200(a):
         dom = frame.prepare_domain(frames_h.to(dev, non_blocking=True), HEADER, origin=origins, nbody=a.nbody)
         s = sampler.GibbsSampler(dom, init_h.to(dev, non_blocking=True), fo_h.to(dev, non_blocking=True),
                                  seed=a.seed + seed_offset, burn_in=0, thin=a.thin,
-                                 id_base=rank * W, id_stride=1)
+                                 id_base=rank * W, id_stride=1, team_warps=a.team)
         return dom, s
 
     dom, smp = make_sampler()
@@ -261,35 +263,43 @@ def run_b200(a):
     value = updates * S * S / secs
 
     # ---- end to end through the public API, host buffers in, host buffers out --------------
+    # Every e2e step is a NEW batch of epochs: frames, starting points come from pinned host
+    # memory, chain rows and counters go back to pinned host memory.  The sampler handle and
+    # its device buffers are reused (lapf_sampler_reset), as a service processing a stream of
+    # epochs would.
     e2e = None
     if not a.no_e2e:
         chain_h = torch.empty((max(rows, 1), W, P + 1), dtype=torch.float64).pin_memory()
         tot_h = torch.empty((2 * P + 1,), dtype=torch.int64).pin_memory()
-        h2d = frames_h.numel() * 4 + init_h.numel() * 8 + fo_h.numel() * 4
+        frames_d = torch.empty_like(frames_h, device=dev)
+        init_d = torch.empty_like(init_h, device=dev)
+        h2d = frames_h.numel() * 4 + init_h.numel() * 8
         d2h = chain_h.numel() * 8 + tot_h.numel() * 8
-        n_e2e = max(2, min(a.steps, 5))
+        n_e2e = max(2, min(a.steps, 10))
         times = []
         for i in range(n_e2e + 1):
             torch.cuda.synchronize()
             dist.barrier()
             t0 = time.perf_counter()
-            d2, s2 = make_sampler(seed_offset=i + 1)
-            ch = s2.run(U, out=chain)
+            frames_d.copy_(frames_h, non_blocking=True)
+            init_d.copy_(init_h, non_blocking=True)
+            frame.prepare_domain(frames_d, HEADER, origin=origins, nbody=a.nbody, into=dom)
+            smp.reset(init_d, seed=a.seed + 1 + i)
+            ch = smp.run(U, out=chain)
             chain_h.copy_(ch, non_blocking=True)
-            stt = s2.stats(moments=False)
+            stt = smp.stats(moments=False)
             tot_h.copy_(torch.cat([stt["tries"], stt["accepts"], stt["min_tries"].reshape(1)]), non_blocking=True)
             torch.cuda.synchronize()
-            s2.close()
             dist.barrier()
             if i > 0:
                 times.append(time.perf_counter() - t0)
-            del d2, s2
         t_e2e = float(dist.allreduce_max(torch.tensor([sum(times)], dtype=torch.float64, device=dev)).item())
         e2e = {"value": float(W) * U * n_e2e * world * S * S / t_e2e, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * t_e2e / n_e2e, "steps": n_e2e,
-               "what": "pinned host frames+initial parameters -> H2D -> frame prep -> sampler create -> "
-                       "%d updates -> chain rows + counters D2H to pinned host -> destroy; wall clock" % U}
+               "what": "per step a new batch: pinned host frames + starting points -> H2D -> frame prep "
+                       "(mask, noise map) -> sampler reset (initial chi-square) -> %d updates -> chain rows "
+                       "+ counters D2H to pinned host; wall clock, max over ranks" % U}
 
     smp.close()
     if rank != 0:
@@ -323,7 +333,7 @@ def run_b200(a):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "gibbs_updates_per_sec": updates / secs,
         "config": {"workload": workload_name(a), "walkers_per_gpu": W, "frames": F, "stamp": S,
-                   "nbody": a.nbody, "updates_per_step": U, "thin": a.thin,
+                   "nbody": a.nbody, "updates_per_step": U, "thin": a.thin, "team_warps": a.team,
                    "l2": "flushed between timed steps (256 MiB memset outside the event pairs); stamps are "
                          "re-staged from HBM into shared memory by TMA in every launch",
                    "timing": "CUDA events around each step on the launch stream, summed; max over ranks",

@@ -103,6 +103,13 @@ int lapf_model_chi2(const lapf_problem* prob, const double* params, int64_t B,
 int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream);
 int lapf_sampler_destroy(lapf_sampler* s);
 
+/* Start a new batch in an existing sampler: new starting points (device [n_walkers][P]) and seed,
+ * counters, moments and update count back to zero, initial chi-square re-evaluated against the
+ * CURRENT contents of the problem's data/weight buffers (which the caller may have overwritten
+ * with new frames of the same shape).  frame_of, widths, burn_in and thin are kept.  Lets a
+ * stream of epochs reuse one handle without reallocating device memory. */
+int lapf_sampler_reset(lapf_sampler* s, const double* init_params, uint64_t seed, void* stream);
+
 /* Chain rows a run of n_updates starting at the sampler's current count will produce. */
 int64_t lapf_sampler_rows_for(const lapf_sampler* s, int64_t n_updates);
 

@@ -40,6 +40,8 @@ def _parser(kind):
     ap.add_argument("--thin", type=int, default=1, help="record every thin-th update (1 = reference)")
     ap.add_argument("--seed", type=int, default=None, help="random seed (default: from the OS, like the reference's unseeded numpy)")
     ap.add_argument("--segment", type=int, default=4096, help="updates per kernel launch")
+    ap.add_argument("--team", type=int, default=0, choices=[0, 1, 4, 16],
+                    help="warps cooperating on one walker (0: pick from the total walker count)")
     ap.add_argument("--format", choices=["csv", "bin"], default="csv", help="per-walker reference CSV files, or one packed binary")
     ap.add_argument("--fix-bkgd", action="store_true",
                     help="2-body only: use bkgd (p[9]) as the constant floor instead of the reference's p[12]")
@@ -110,8 +112,13 @@ def run(kind, nbody, argv=None):
     say("Random seed:", seed)
     if n_local == 0:
         say("rank has no walkers")
+    # Few walkers: several warps per walker, so one update takes 1/16 of the time.  The choice
+    # depends on the TOTAL walker count only, so every rank makes the same one.
+    team = args.team
+    if team == 0:
+        team = 16 if (total_walkers <= 1200 * world and args.stamp >= 64) else (4 if total_walkers <= 4800 * world else 1)
     sam = smp.GibbsSampler(dom, np.tile(parameters, (max(n_local, 1), 1)), seed=seed, burn_in=burn_in,
-                           thin=args.thin, id_base=id_base, id_stride=id_stride)
+                           thin=args.thin, id_base=id_base, id_stride=id_stride, team_warps=team)
     st0, _, _ = sam.state()
     say("Found initial chi-squared:", float(st0[0, -1].item()))
     say("Initial guess:", np.concatenate([parameters, [float(st0[0, -1].item())]]))

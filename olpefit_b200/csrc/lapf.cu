@@ -236,9 +236,15 @@ struct RunArgs {
     int thin, floor_index, n_items;
 };
 
-template <int NB, int NX, int NY>
+// One walker for n_updates updates.  TEAM = 1: one warp does everything.  TEAM > 1 (few walkers,
+// latency matters): TEAM warps run this function for the SAME walker in lock-step; each repeats the
+// cheap scalar part (identical inputs, identical results), evaluates its share of the rows, and the
+// partial chi-squares meet in shared memory behind one named barrier per update.  Only warp 0 of
+// the team writes counters, chain rows and the final state.
+template <int NB, int NX, int NY, int TEAM>
 __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, const float* sw,
-                                           WarpScratch& ws, float* rt, int wl, int frame, int lane) {
+                                           WarpScratch& ws, float* rt, double* team_part, int team,
+                                           int tw, int wl, int frame, int lane) {
     using L = Layout<NB>;
     constexpr int P = L::P;
     const uint64_t gid = (uint64_t)(a.id_base + (int64_t)wl * a.id_stride);
@@ -293,11 +299,19 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         const int which = (k == L::I_SX2 || k == L::I_SY2 || k == L::I_TH2) ? 1 : 0;
         if (shape_moved) load_shape<NB>(cf, which, ws.tf);
         build_row_table<NB, NY>(rt, cf, lane);
-        const double chi_t = warp_chi2<NB, NX, NY, false, true>(cf, rt, sd, sw, nullptr, lane);   // :314-316
+        double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw);   // :314-316
+        if (TEAM > 1) {
+            double* slot_p = team_part + (u & 1) * TEAM;       // double-buffered: one barrier per update
+            if (lane == 0) slot_p[tw] = chi_t;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TEAM * 32) : "memory");
+            chi_t = 0.0;
+#pragma unroll
+            for (int t = 0; t < TEAM; ++t) chi_t += slot_p[t];  // same order in every warp of the team
+        }
 
         // accept iff u < exp(-(chi_t - chi_c)/2) (apf_step2.py:139-148); false on nan
         const bool acc = ws.lnu[slot] < -0.5 * (chi_t - chi_c);
-        if (lane == 0) {
+        if (lane == 0 && tw == 0) {
             atomicAdd(&a.tries[(size_t)wl * P + k], 1u);              // :304
             if (acc) atomicAdd(&a.accepts[(size_t)wl * P + k], 1u);   // :323
         }
@@ -310,7 +324,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
             }
         }
         if (a.t0 + u + 1 == next_rec) {                               // :342-351
-            if (lane <= P) {
+            if (lane <= P && tw == 0) {
                 const size_t mi = (size_t)wl * (P + 1) + lane;
                 const double v = (lane == P) ? chi_c : p;
                 if (a.chain) a.chain[((size_t)row * a.n_walkers + wl) * (P + 1) + lane] = v;
@@ -323,14 +337,18 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         }
     }
 
-    if (lane < P) st[lane] = p;
-    if (lane == P) st[P] = chi_c;
+    if (tw == 0) {
+        if (lane < P) st[lane] = p;
+        if (lane == P) st[P] = chi_c;
+    }
 }
 
-template <int NB, int NX, int NY, int NW, int MINB>
+template <int NB, int NX, int NY, int NW, int MINB, int TEAM>
 __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_constant__ RunArgs a) {
+    static_assert(NW % TEAM == 0 && (TEAM == 1 || NW / TEAM <= 15), "teams must tile the CTA (named barriers 1..15)");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ WarpScratch scratch[NW];
+    __shared__ double team_part[NW / TEAM][2 * TEAM];
     __shared__ uint64_t bar;
     float* sd = reinterpret_cast<float*>(smem_raw);
     float* sw = sd + NX * NY;
@@ -362,9 +380,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
             prep_stamp(sd, sw, NX * NY);            // (d, w) -> (d*sqrt(w), -sqrt(w)), once per staged frame
             __syncthreads();
         }
-        if (warp < a.item_count[it])
-            run_walker<NB, NX, NY>(a, sd, sw, scratch[warp], rt + warp * (NY * 4 * NB),
-                                   a.walker_of[a.item_first[it] + warp], f, lane);
+        const int team = warp / TEAM, tw = warp % TEAM;
+        if (team < a.item_count[it])
+            run_walker<NB, NX, NY, TEAM>(a, sd, sw, scratch[warp], rt + warp * (NY * 4 * NB), team_part[team],
+                                         team, tw, a.walker_of[a.item_first[it] + team], f, lane);
     }
 }
 
@@ -519,7 +538,7 @@ struct lapf_sampler {
     lapf_config cfg;
     int P = 0;
     int device = 0;
-    int nw = 0, minb = 0, grid = 0;
+    int nw = 0, minb = 0, grid = 0, team = 1;
     size_t smem = 0;
     int64_t count = 0;      // updates done so far
     int64_t launches = 0;
@@ -660,10 +679,10 @@ int lapf_model_chi2(const lapf_problem* prob, const double* params, int64_t B, c
 // sampler
 // ---------------------------------------------------------------------------------------------
 extern "C++" {
-template <int NB, int NX, int NW, int MINB>
+template <int NB, int NX, int NW, int MINB, int TEAM>
 static int configure_gibbs(lapf_sampler* s) {
-    auto kern = gibbs_kernel<NB, NX, NX, NW, MINB>;
-    s->nw = NW;
+    auto kern = gibbs_kernel<NB, NX, NX, NW, MINB, TEAM>;
+    s->nw = NW / TEAM;   // walkers per CTA item
     s->minb = MINB;
     s->smem = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * NX * 4 * NB;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
@@ -675,24 +694,31 @@ static int configure_gibbs(lapf_sampler* s) {
     return LAPF_OK;
 }
 
-template <int NB, int NX, int NW, int MINB>
+template <int NB, int NX, int NW, int MINB, int TEAM>
 static int launch_gibbs(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
     const int grid = std::min(s->grid, a.n_items);
-    gibbs_kernel<NB, NX, NX, NW, MINB><<<grid, NW * 32, s->smem, st>>>(a);
+    gibbs_kernel<NB, NX, NX, NW, MINB, TEAM><<<grid, NW * 32, s->smem, st>>>(a);
     CU(cudaGetLastError());
     return LAPF_OK;
 }
 
+#define LAPF_DISPATCH_TEAM(FN, NB_, NX_, NW_, ...)                                          \
+    do {                                                                                    \
+        if (s->team == 1) return FN<NB_, NX_, NW_, 1, 1>(__VA_ARGS__);                      \
+        if (s->team == 4) return FN<NB_, NX_, NW_, 1, 4>(__VA_ARGS__);                      \
+        if (s->team == 16 && NX_ >= 64 && NW_ == 16) return FN<NB_, NX_, 16, 1, (NX_ >= 64 ? 16 : 4)>(__VA_ARGS__); \
+    } while (0)
+
 #define LAPF_DISPATCH_GIBBS(FN, ...)                                                        \
     do {                                                                                    \
         const int nb__ = s->cfg.problem.nbody, nx__ = s->cfg.problem.nx;                    \
-        if (nb__ == 2 && nx__ == 32) return FN<2, 32, 16, 1>(__VA_ARGS__);                   \
-        if (nb__ == 2 && nx__ == 64) return FN<2, 64, 16, 1>(__VA_ARGS__);                   \
-        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 16, 1>(__VA_ARGS__);                \
-        if (nb__ == 3 && nx__ == 32) return FN<3, 32, 16, 1>(__VA_ARGS__);                   \
-        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 16, 1>(__VA_ARGS__);                   \
-        if (nb__ == 3 && nx__ == 128) return FN<3, 128, 12, 1>(__VA_ARGS__);                \
-        return fail(LAPF_ERR_INVALID, "unsupported sampler shape nbody=%d nx=%d", nb__, nx__); \
+        if (nb__ == 2 && nx__ == 32) LAPF_DISPATCH_TEAM(FN, 2, 32, 16, __VA_ARGS__);        \
+        if (nb__ == 2 && nx__ == 64) LAPF_DISPATCH_TEAM(FN, 2, 64, 16, __VA_ARGS__);        \
+        if (nb__ == 2 && nx__ == 128) LAPF_DISPATCH_TEAM(FN, 2, 128, 16, __VA_ARGS__);      \
+        if (nb__ == 3 && nx__ == 32) LAPF_DISPATCH_TEAM(FN, 3, 32, 16, __VA_ARGS__);        \
+        if (nb__ == 3 && nx__ == 64) LAPF_DISPATCH_TEAM(FN, 3, 64, 16, __VA_ARGS__);        \
+        if (nb__ == 3 && nx__ == 128) LAPF_DISPATCH_TEAM(FN, 3, 128, 12, __VA_ARGS__);      \
+        return fail(LAPF_ERR_INVALID, "unsupported sampler shape nbody=%d nx=%d team_warps=%d", nb__, nx__, s->team); \
     } while (0)
 
 static int configure_dispatch(lapf_sampler* s) { LAPF_DISPATCH_GIBBS(configure_gibbs, s); }
@@ -722,8 +748,8 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     if (!cfg->init_params) return fail(LAPF_ERR_INVALID, "init_params is NULL");
     if (cfg->thin < 1) return fail(LAPF_ERR_INVALID, "thin must be >= 1");
     if (cfg->burn_in < 0) return fail(LAPF_ERR_INVALID, "burn_in must be >= 0");
-    if (cfg->team_warps != 0 && cfg->team_warps != 1)
-        return fail(LAPF_ERR_INVALID, "team_warps %d not supported (0 or 1)", cfg->team_warps);
+    if (cfg->team_warps != 0 && cfg->team_warps != 1 && cfg->team_warps != 4 && cfg->team_warps != 16)
+        return fail(LAPF_ERR_INVALID, "team_warps %d not supported (0, 1, 4 or 16)", cfg->team_warps);
     if ((rc = require_device())) return rc;
     cudaStream_t st = (cudaStream_t)stream;
 
@@ -731,6 +757,7 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     if (!s) return fail(LAPF_ERR_NOMEM, "out of host memory");
     s->cfg = *cfg;
     s->P = 3 * pb.nbody + 10;
+    s->team = cfg->team_warps ? cfg->team_warps : 1;
     const int P = s->P;
     const int64_t W = cfg->n_walkers;
     cudaGetDevice(&s->device);
@@ -794,24 +821,35 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     CUS(cudaMemcpyAsync(s->item_frame, it_frame.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
     CUS(cudaMemcpyAsync(s->item_first, it_first.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
     CUS(cudaMemcpyAsync(s->item_count, it_count.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
-    CUS(cudaMemsetAsync(s->moments, 0, sizeof(double) * nst * 2, st));
-    CUS(cudaMemsetAsync(s->tries, 0, sizeof(uint32_t) * W * P, st));
-    CUS(cudaMemsetAsync(s->accepts, 0, sizeof(uint32_t) * W * P, st));
 
-    // initial chi-square (apf_step2.py:283-289) through K1, then pack the state
-    double* chi0 = nullptr;
-    CUS(cudaMallocAsync((void**)&chi0, sizeof(double) * W, st));
-    rc = lapf_model_chi2(&pb, cfg->init_params, W, cfg->frame_of, nullptr, chi0, st);
+    CUS(cudaStreamSynchronize(st));   // the host vectors above are pageable
+    rc = lapf_sampler_reset(s, cfg->init_params, cfg->seed, st);
     if (rc) { free_sampler(s); return rc; }
-    s->launches++;
-    pack_state_kernel<<<(unsigned)((nst + 255) / 256), 256, 0, st>>>(cfg->init_params, chi0, P, W, s->state, s->shift);
-    CUS(cudaGetLastError());
-    CUS(cudaFreeAsync(chi0, st));
-    // the host vectors above are pageable: make sure the copies have consumed them
-    CUS(cudaStreamSynchronize(st));
-    s->launches++;
 #undef CUS
     *out = s;
+    return LAPF_OK;
+}
+
+int lapf_sampler_reset(lapf_sampler* s, const double* init_params, uint64_t seed, void* stream) {
+    if (!s || !init_params) return fail(LAPF_ERR_INVALID, "sampler/init_params is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = s->P;
+    const int64_t W = s->cfg.n_walkers;
+    const size_t nst = (size_t)W * (P + 1);
+    CU(cudaMemsetAsync(s->moments, 0, sizeof(double) * nst * 2, st));
+    CU(cudaMemsetAsync(s->tries, 0, sizeof(uint32_t) * W * P, st));
+    CU(cudaMemsetAsync(s->accepts, 0, sizeof(uint32_t) * W * P, st));
+    // initial chi-square (apf_step2.py:283-289) through K1, then pack the state
+    double* chi0 = nullptr;
+    CU(cudaMallocAsync((void**)&chi0, sizeof(double) * W, st));
+    int rc = lapf_model_chi2(&s->cfg.problem, init_params, W, s->cfg.frame_of, nullptr, chi0, st);
+    if (rc) { cudaFreeAsync(chi0, st); return rc; }
+    pack_state_kernel<<<(unsigned)((nst + 255) / 256), 256, 0, st>>>(init_params, chi0, P, W, s->state, s->shift);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(chi0, st));
+    s->launches += 2;
+    s->cfg.seed = seed;
+    s->count = 0;
     return LAPF_OK;
 }
 

@@ -227,15 +227,20 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
 // instruction, scalar coefficients as broadcast operands.  Per pixel PAIR and component that is
 // 3 FFMA2 + 2 MUFU.EX2, which keeps the issue slots needed per MUFU below the SFU's own rate
 // (measured: a MUFU costs ~4 issue cycles), so the loop is SFU-bound.
-template <int NB, int NX, int NY, bool STORE, bool PREP>
+//
+// TEAM > 1: TEAM warps share one parameter vector; warp `tw` of the team takes every TEAM-th row
+// step and returns ITS partial sum (the caller combines the partials in a fixed order).
+template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1>
 __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __restrict__ rt,
                                             const float* __restrict__ d, const float* __restrict__ w,
-                                            float* __restrict__ model_out, int lane) {
+                                            float* __restrict__ model_out, int lane, int tw = 0) {
     using G = Geo<NX>;
     constexpr int K = 2 * NB;
     constexpr int STEPS = NY / G::RG;            // row steps per panel
-    constexpr int FOLD = STEPS % 4 == 0 ? 4 : 1; // FP32 partials are folded into FP64 every FOLD steps
+    // FP32 partials are folded into FP64 every FOLD steps
+    constexpr int FOLD = (TEAM == 1 && STEPS % 4 == 0) ? 4 : 1;
     static_assert(NY % G::RG == 0, "unsupported stamp height");
+    static_assert(STEPS % (TEAM * FOLD) == 0, "team size must divide the row steps");
     const int c = lane % G::LPR, g = lane / G::LPR;
     const int swap = (G::PW == 32) ? (g & 1) : 0;
     double acc = 0.0;
@@ -252,12 +257,14 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
                 xd[k][2 + jj] = make_float2((float)(colB + 2 * jj) - cf.x0[k], (float)(colB + 2 * jj + 1) - cf.x0[k]);
             }
         }
-        const float* rp = rt + g * 2 * K;
-        const float* dp = d + g * NX;
-        const float* wp = w + g * NX;
-        float* mp = STORE ? model_out + g * NX : nullptr;
+        const int r0 = g + tw * FOLD * G::RG;    // first row of this warp
+        const float* rp = rt + r0 * 2 * K;
+        const float* dp = d + r0 * NX;
+        const float* wp = w + r0 * NX;
+        float* mp = STORE ? model_out + r0 * NX : nullptr;
+        constexpr int SKIP = (TEAM - 1) * FOLD * G::RG;   // rows that belong to the other warps of the team
 #pragma unroll 1
-        for (int ib = 0; ib < STEPS; ib += FOLD) {
+        for (int ib = tw * FOLD; ib < STEPS; ib += TEAM * FOLD) {
             float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll 1
             for (int ii = 0; ii < FOLD; ++ii) {
@@ -317,6 +324,12 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
                 wp += G::RG * NX;
             }
             acc += (double)((s0.x + s0.y) + (s1.x + s1.y));
+            if (TEAM > 1) {
+                rp += SKIP * 2 * K;
+                dp += SKIP * NX;
+                wp += SKIP * NX;
+                if (STORE) mp += SKIP * NX;
+            }
         }
     }
     return warp_sum_f64(acc);

@@ -155,7 +155,7 @@ def read_noise(header) -> float:
 # device frame preparation
 # ----------------------------------------------------------------------------------------------
 def prepare_domain(frames, header, size=None, cut=None, origin=None, nbody=2, floor_index=None,
-                   device="cuda") -> PixelDomain:
+                   device="cuda", into: PixelDomain = None) -> PixelDomain:
     """Mask (image > 0.8*satlevel, apf_step2.py:188), noise map (err^2 = readnoise^2 + |image|,
     :197-210) and cut-outs, all on the device.
 
@@ -163,11 +163,13 @@ def prepare_domain(frames, header, size=None, cut=None, origin=None, nbody=2, fl
     origin  frame coordinates (x0, y0) of frames[f][0][0]: one pair or [F, 2]; default (0, 0)
     cut     (x, y) of the cut-out inside each array: one pair or [F, 2]; default (0, 0)
     size    cut-out size, an int or (ny, nx); default: the whole array
+    into    an existing PixelDomain of the same shape whose pixel buffers are overwritten in place
+            (a new batch of epochs for a sampler that is then ``reset``)
     """
     lib = _lib.load()
     if not torch.cuda.is_available():
         raise _lib.LapfError("no CUDA device: olpefit_b200 has no CPU path")
-    dev = torch.device(device)
+    dev = into.device if into is not None else torch.device(device)
     fr = frames if torch.is_tensor(frames) else torch.as_tensor(np.ascontiguousarray(frames, dtype=np.float32))
     if fr.dim() == 2:
         fr = fr[None]
@@ -184,11 +186,19 @@ def prepare_domain(frames, header, size=None, cut=None, origin=None, nbody=2, fl
 
     cut_np, org_np = pairs(cut), pairs(origin)
     cut_t = torch.as_tensor(cut_np.astype(np.int32)).to(dev)
-    data = torch.empty((nf, ny, nx), dtype=torch.float32, device=dev)
-    weight = torch.empty_like(data)
+    if into is not None:
+        if (into.n_frames, into.ny, into.nx) != (nf, ny, nx):
+            raise ValueError("into has shape %s, new frames give %s" % ((into.n_frames, into.ny, into.nx), (nf, ny, nx)))
+        data, weight = into.data, into.weight
+    else:
+        data = torch.empty((nf, ny, nx), dtype=torch.float32, device=dev)
+        weight = torch.empty_like(data)
     _lib.check(lib.lapf_frame_prep(fr.data_ptr(), nf, fy, fx, cut_t.data_ptr(), ny, nx,
                                    float(saturation_level(header)), float(read_noise(header)),
                                    data.data_ptr(), weight.data_ptr(), _stream_ptr(dev)))
+    if into is not None:
+        into.origin.copy_(torch.as_tensor((org_np + cut_np).astype(np.int32)))
+        return into
     return PixelDomain(data, weight, (org_np + cut_np).astype(np.int32), nbody=nbody,
                        floor_index=floor_index, device=device)
 

@@ -67,6 +67,19 @@ class GibbsSampler:
     def __exit__(self, *exc):
         self.close()
 
+    def reset(self, init_params, seed=0):
+        """Start a new batch in this sampler: new starting points and seed; counters, moments
+        and the update count return to zero and the initial chi-square is re-evaluated against
+        the domain's current pixel buffers (see ``frame.prepare_domain(into=...)``)."""
+        dev = self.domain.device
+        p = init_params if torch.is_tensor(init_params) else torch.as_tensor(np.asarray(init_params, dtype=np.float64))
+        p = p.to(dev, torch.float64).reshape(-1, self.nparam).contiguous()
+        if p.shape[0] != self.n_walkers:
+            raise ValueError("init_params must have one row per walker")
+        self._keep = (p, self._keep[1])
+        _lib.check(self.lib.lapf_sampler_reset(self._h, p.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                               _stream_ptr(dev)))
+
     # -- the loop ------------------------------------------------------------------------
     @property
     def count(self) -> int:

@@ -167,8 +167,9 @@ def _sampler_setup(gpu, nbody, size, n_frames=1):
     return dom, stamps, origins, p0
 
 
-@pytest.mark.parametrize("nbody,size", [(2, 32), (2, 64), (3, 32), (2, 128)])
-def test_sampler_replays_oracle_stream(gpu, nbody, size):
+@pytest.mark.parametrize("nbody,size,team", [(2, 32, 1), (2, 64, 1), (3, 32, 1), (2, 128, 1), (3, 64, 1),
+                                             (2, 64, 4), (2, 64, 16), (2, 32, 4), (3, 128, 4), (2, 128, 16)])
+def test_sampler_replays_oracle_stream(gpu, nbody, size, team):
     """Same Philox stream on both sides: the device chain must follow the float64 oracle chain
     update by update (same parameter picked, same decision, same values) until FP32 rounding of
     chi-square flips a borderline accept -- which must not happen early."""
@@ -176,7 +177,8 @@ def test_sampler_replays_oracle_stream(gpu, nbody, size):
     dom, stamps, origins, p0 = _sampler_setup(gpu, nbody, size)
     n_upd, walkers, seed = 240, 3, 1234
     init = np.tile(p0, (walkers, 1))
-    with gpu["sampler"].GibbsSampler(dom, init, seed=seed, burn_in=0, thin=1, id_base=5, id_stride=3) as s:
+    with gpu["sampler"].GibbsSampler(dom, init, seed=seed, burn_in=0, thin=1, id_base=5, id_stride=3,
+                                     team_warps=team) as s:
         chain = s.run(n_upd).cpu().numpy()
         st, tries, accepts = (t.cpu().numpy() for t in s.state())
     img = stamps[0].astype(np.float64)
@@ -285,3 +287,27 @@ def test_sampler_moments_match_chain(gpu):
         np.testing.assert_allclose(mom[f, :, 0], means.sum(axis=0), rtol=1e-10)
         np.testing.assert_allclose(mom[f, :, 1], (means ** 2).sum(axis=0), rtol=1e-10)
         np.testing.assert_allclose(mom[f, :, 2], (sub.std(axis=0) ** 2).sum(axis=0), rtol=1e-6, atol=1e-12)
+
+
+def test_team_mode_agrees_with_single_warp_mode(gpu):
+    """Several warps per walker change only the order of the FP64 partial sums: chi-square agrees
+    to rounding, and the chains stay together until a borderline accept flips (not within the first
+    updates).  Split runs and sharding stay bitwise reproducible for a fixed team size."""
+    torch = gpu["torch"]
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 64, n_frames=2)
+    walkers = 21
+    init = np.tile(p0, (walkers, 1))
+    frame_of = (np.arange(walkers) % 2).astype(np.int32)
+    out = {}
+    for team in (1, 4, 16):
+        with gpu["sampler"].GibbsSampler(dom, init, frame_of, seed=8, team_warps=team) as s:
+            out[team] = s.run(150)
+            st, tries, acc = s.state()
+            assert int(tries.sum()) == 150 * walkers
+        with gpu["sampler"].GibbsSampler(dom, init, frame_of, seed=8, team_warps=team) as s:
+            again = torch.cat([s.run(60), s.run(90)], dim=0)
+        assert torch.equal(out[team], again)
+    for team in (4, 16):
+        a, b = out[1].cpu().numpy(), out[team].cpu().numpy()
+        np.testing.assert_allclose(a[:40], b[:40], rtol=1e-9)
+        assert np.mean(np.isclose(a, b, rtol=1e-9)) > 0.9
