@@ -309,5 +309,6 @@ def test_team_mode_agrees_with_single_warp_mode(gpu):
         assert torch.equal(out[team], again)
     for team in (4, 16):
         a, b = out[1].cpu().numpy(), out[team].cpu().numpy()
-        np.testing.assert_allclose(a[:40], b[:40], rtol=1e-9)
-        assert np.mean(np.isclose(a, b, rtol=1e-9)) > 0.9
+        np.testing.assert_allclose(a[:40, :, :-1], b[:40, :, :-1], rtol=1e-9)   # same decisions, same values
+        np.testing.assert_allclose(a[:40, :, -1], b[:40, :, -1], rtol=1e-6)     # chi-square: FP32 partials regrouped
+        assert np.mean(np.isclose(a[..., :-1], b[..., :-1], rtol=1e-9)) > 0.9
