@@ -166,6 +166,13 @@ int lapf_frame_prep(const float* frames, int32_t n_frames, int32_t fy, int32_t f
                     const int32_t* origin, int32_t ny, int32_t nx, double satlevel,
                     double readnoise, float* data_out, float* weight_out, void* stream);
 
+/* The sampler's random stream for updates first_update .. first_update+n-1 of one walker, in the
+ * reference's draw order (apf_step2.py:302 index, :64/:68 normal, :143 uniform): parameter index,
+ * standard normal, natural log of the uniform.  Device outputs of length n.  Philox4x32-10 with
+ * key = (seed low 32 bits, walker id) and counter = (update low, update high, seed high, 'LAPF'). */
+int lapf_philox_draws(uint64_t seed, uint64_t walker_id, uint64_t first_update, int32_t n, int32_t nparam,
+                      int32_t* index_out, double* normal_out, double* log_uniform_out, void* stream);
+
 /* Micro-benchmarks for the roofline denominators: issue rates of MUFU.EX2 and FFMA on the
  * current device.  Synchronous.  out[0] = ex2 results/s, out[1] = FFMA lane-ops/s,
  * out[2] = SM clock (MHz) reported by the driver, out[3] = SM count. */

@@ -48,6 +48,8 @@ SYMBOLS = {
     "lapf_write_chain_csv": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32]),
     "lapf_frame_prep": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                   C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lapf_philox_draws": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "lapf_measure_peaks": (C.c_int, [C.POINTER(C.c_double)]),
 }
 

@@ -469,6 +469,18 @@ __global__ void counts_kernel(const int32_t* __restrict__ frame_start, int F, in
     if (i == F) out[F] = n_rows;
 }
 
+// The sampler's random stream, exposed so tests can pin it against the oracle's restatement.
+__global__ void philox_draws_kernel(uint64_t seed, uint64_t walker, uint64_t t0, int n, int nparam,
+                                    int32_t* __restrict__ k_out, double* __restrict__ z_out,
+                                    double* __restrict__ lnu_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Draw d = make_draw(seed, walker, t0 + (uint64_t)i, nparam);
+    k_out[i] = d.k;
+    z_out[i] = d.z;
+    lnu_out[i] = d.lnu;
+}
+
 // =============================================================================================
 // frame preparation (apf_step2.py:176-210) + cut-out
 // =============================================================================================
@@ -993,6 +1005,19 @@ int lapf_frame_prep(const float* frames, int32_t n_frames, int32_t fy, int32_t f
     const int64_t n = (int64_t)n_frames * ny * nx;
     frame_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         frames, n_frames, fy, fx, origin, ny, nx, 0.8 * satlevel, readnoise * readnoise, data_out, weight_out);
+    CU(cudaGetLastError());
+    return LAPF_OK;
+}
+
+int lapf_philox_draws(uint64_t seed, uint64_t walker_id, uint64_t first_update, int32_t n, int32_t nparam,
+                      int32_t* index_out, double* normal_out, double* log_uniform_out, void* stream) {
+    if (n < 0 || nparam <= 0 || !index_out || !normal_out || !log_uniform_out)
+        return fail(LAPF_ERR_INVALID, "bad arguments to lapf_philox_draws");
+    if (n == 0) return LAPF_OK;
+    int rc = require_device();
+    if (rc) return rc;
+    philox_draws_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, walker_id, first_update, n, nparam,
+                                                                          index_out, normal_out, log_uniform_out);
     CU(cudaGetLastError());
     return LAPF_OK;
 }

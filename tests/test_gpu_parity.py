@@ -312,3 +312,25 @@ def test_team_mode_agrees_with_single_warp_mode(gpu):
         np.testing.assert_allclose(a[:40, :, :-1], b[:40, :, :-1], rtol=1e-9)   # same decisions, same values
         np.testing.assert_allclose(a[:40, :, -1], b[:40, :, -1], rtol=1e-6)     # chi-square: FP32 partials regrouped
         assert np.mean(np.isclose(a[..., :-1], b[..., :-1], rtol=1e-9)) > 0.9
+
+
+def test_device_random_stream_equals_oracle_stream(gpu):
+    """The Philox stream is defined once and restated by the oracle: same
+    parameter index, same normal and uniform (to double rounding) for every update."""
+    import math
+    torch = gpu["torch"]
+    from olpefit_b200 import _lib
+    lib = _lib.load()
+    for seed, walker, t0, npar in ((1234, 5, 0, 16), (2 ** 40 + 17, 70000, 2 ** 33, 19)):
+        n = 300
+        k = torch.empty(n, dtype=torch.int32, device="cuda")
+        z = torch.empty(n, dtype=torch.float64, device="cuda")
+        lnu = torch.empty(n, dtype=torch.float64, device="cuda")
+        _lib.check(lib.lapf_philox_draws(seed, walker, t0, n, npar, k.data_ptr(), z.data_ptr(), lnu.data_ptr(), None))
+        k, z, lnu = k.cpu().numpy(), z.cpu().numpy(), lnu.cpu().numpy()
+        for i in range(n):
+            ko, zo, uo = orc.device_draws(seed, walker, t0 + i, npar)
+            assert k[i] == ko
+            assert z[i] == pytest.approx(zo, rel=1e-12, abs=1e-14)
+            assert lnu[i] == pytest.approx(math.log(uo) if uo > 0 else -math.inf, rel=1e-13)
+        assert set(k.tolist()) == set(range(npar))
