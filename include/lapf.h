@@ -60,6 +60,12 @@ typedef struct lapf_problem {
     const float* data;      /* device [F][ny][nx]; finite everywhere (0 on masked pixels) */
     const float* weight;    /* device [F][ny][nx] */
     const int32_t* origin;  /* device [F][2]: frame coordinates (x0, y0) of pixel [0][0] */
+    const double* outside;  /* device [F][3] or NULL.  When the frames are cut-outs of larger images:
+                               sum w, sum w*d, sum w*d^2 over the image pixels OUTSIDE the cut-out.
+                               There the reference's model is the constant floor f (the Gaussians
+                               are below double rounding), so those pixels add
+                               S2 - 2 f S1 + f^2 S0 to chi-square: with this set, chi-square is the
+                               reference's whole-frame value (apf_step2.py:94,134-137) at stamp cost */
 } lapf_problem;
 
 /* Configuration of a batch of independent walkers (replaces "one MPI rank per walker",

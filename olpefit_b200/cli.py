@@ -37,6 +37,9 @@ def _parser(kind):
     ap.add_argument("--burn-in", type=int, default=None)
     ap.add_argument("--stamp", type=int, default=64, choices=[32, 64, 128],
                     help="side of the square pixel domain centred on the objects")
+    ap.add_argument("--domain", choices=["frame", "stamp"], default="frame",
+                    help="frame: chi-square over the whole image like the reference (pixels outside the stamp enter "
+                         "through their exact sums against the constant floor); stamp: the cut-out only")
     ap.add_argument("--thin", type=int, default=1, help="record every thin-th update (1 = reference)")
     ap.add_argument("--seed", type=int, default=None, help="random seed (default: from the OS, like the reference's unseeded numpy)")
     ap.add_argument("--segment", type=int, default=4096, help="updates per kernel launch")
@@ -98,7 +101,8 @@ def run(kind, nbody, argv=None):
     floor_index = layout.bkgd_index(nbody) if (args.fix_bkgd and nbody == 2) else layout.REFERENCE_FLOOR_INDEX
     ox, oy = _stamp_origin(parameters, nbody, args.stamp, image.shape)
     dom = frame.prepare_domain(image.astype(np.float32), hdr, size=args.stamp, cut=(ox, oy), nbody=nbody,
-                               floor_index=floor_index, device="cuda:%d" % local_rank)
+                               floor_index=floor_index, device="cuda:%d" % local_rank,
+                               whole_frame=(args.domain == "frame"))
     say("I have masked", int((dom.weight == 0).sum().item()), "pixels (inside the %dx%d domain at x0=%d y0=%d)"
         % (args.stamp, args.stamp, ox, oy))
 

@@ -81,8 +81,15 @@ struct ProbPtrs {
     const float* data;
     const float* weight;
     const int32_t* origin;
+    const double* outside;   // [F][3] or nullptr (see lapf_problem.outside)
     int n_frames, floor_index;
 };
+
+// chi-square of the image pixels outside the cut-out, where the model is the constant floor f
+__device__ __forceinline__ double outside_chi2(const double* __restrict__ outside, int frame, double f) {
+    const double s0 = outside[3 * frame], s1 = outside[3 * frame + 1], s2 = outside[3 * frame + 2];
+    return fma(f, fma(f, s0, -2.0 * s1), s2);
+}
 
 template <int NB, int NX, int NY, bool STORE>
 __global__ void __launch_bounds__(128)
@@ -108,9 +115,10 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
     __shared__ __align__(16) float rt[4][NY * 4 * NB];
     build_row_table<NB, NY>(rt[warp], cf, lane);
     const size_t off = (size_t)f * NX * NY;
-    const double chi = warp_chi2<NB, NX, NY, STORE, false>(cf, rt[warp], pr.data + off, pr.weight + off,
+    double chi = warp_chi2<NB, NX, NY, STORE, false>(cf, rt[warp], pr.data + off, pr.weight + off,
                                                            STORE ? model_out + (size_t)b * NX * NY : nullptr, lane);
-    if (lane == 0 && chi2_out) chi2_out[b] = chi;
+    if (lane == 0 && chi2_out)
+        chi2_out[b] = pr.outside ? chi + outside_chi2(pr.outside, f, params[b * P + pr.floor_index]) : chi;
 }
 
 // Any (ny, nx), e.g. the reference's whole 1024 x 1024 frame (apf_step2.py:94,237): grid =
@@ -196,6 +204,7 @@ model_chi2_generic_kernel(ProbPtrs pr, int ny, int nx, int rows_per_tile, const 
     if (threadIdx.x == 0 && partial) {
         double s = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        if (tile == 0 && pr.outside) s += outside_chi2(pr.outside, f, pv[pr.floor_index]);
         partial[b * ntile + tile] = s;
     }
 }
@@ -216,6 +225,7 @@ struct RunArgs {
     const float* data;
     const float* weight;
     const int32_t* origin;
+    const double* outside;       // [F][3] or nullptr
     const int32_t* item_frame;   // [n_items]
     const int32_t* item_first;   // [n_items] offset into walker_of
     const int32_t* item_count;   // [n_items] walkers in the item (<= warps per CTA)
@@ -308,6 +318,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
 #pragma unroll
             for (int t = 0; t < TEAM; ++t) chi_t += slot_p[t];  // same order in every warp of the team
         }
+        if (a.outside) chi_t += outside_chi2(a.outside, frame, (k == a.floor_index) ? nv : shfl_f64(p, a.floor_index));
 
         // accept iff u < exp(-(chi_t - chi_c)/2) (apf_step2.py:139-148); false on nan
         const bool acc = ws.lnu[slot] < -0.5 * (chi_t - chi_c);
@@ -658,7 +669,7 @@ int lapf_model_chi2(const lapf_problem* prob, const double* params, int64_t B, c
     if (B == 0) return LAPF_OK;
     if ((rc = require_device())) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    ProbPtrs pr{prob->data, prob->weight, prob->origin, prob->n_frames, prob->floor_index};
+    ProbPtrs pr{prob->data, prob->weight, prob->origin, prob->outside, prob->n_frames, prob->floor_index};
     if (stamp_supported(prob->ny, prob->nx) && (!model_out || ((uintptr_t)model_out & 15) == 0)) {
         if (prob->nbody == 2)
             launch_stamp_k1_size<2>(prob->nx, model_out != nullptr, pr, params, B, frame_of, model_out, chi2_out, st);
@@ -888,7 +899,7 @@ int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int6
         return fail(LAPF_ERR_INVALID, "chain_out holds %lld rows but this run records %lld", (long long)rows_cap, (long long)rows);
     const lapf_problem& pb = s->cfg.problem;
     RunArgs a;
-    a.data = pb.data; a.weight = pb.weight; a.origin = pb.origin;
+    a.data = pb.data; a.weight = pb.weight; a.origin = pb.origin; a.outside = pb.outside;
     a.item_frame = s->item_frame; a.item_first = s->item_first; a.item_count = s->item_count;
     a.walker_of = s->walker_of;
     a.state = s->state; a.shift = s->shift; a.moments = s->moments;

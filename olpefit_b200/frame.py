@@ -155,7 +155,7 @@ def read_noise(header) -> float:
 # device frame preparation
 # ----------------------------------------------------------------------------------------------
 def prepare_domain(frames, header, size=None, cut=None, origin=None, nbody=2, floor_index=None,
-                   device="cuda", into: PixelDomain = None) -> PixelDomain:
+                   device="cuda", into: PixelDomain = None, whole_frame=False) -> PixelDomain:
     """Mask (image > 0.8*satlevel, apf_step2.py:188), noise map (err^2 = readnoise^2 + |image|,
     :197-210) and cut-outs, all on the device.
 
@@ -165,6 +165,11 @@ def prepare_domain(frames, header, size=None, cut=None, origin=None, nbody=2, fl
     size    cut-out size, an int or (ny, nx); default: the whole array
     into    an existing PixelDomain of the same shape whose pixel buffers are overwritten in place
             (a new batch of epochs for a sampler that is then ``reset``)
+    whole_frame
+            also reduce the pixels of each array OUTSIDE its cut-out to (sum w, sum w d, sum w d^2).
+            The reference evaluates chi-square over the whole frame (apf_step2.py:94,134-137); far
+            from the objects its model is the constant floor, so those three sums reproduce the
+            whole-frame chi-square exactly (as a quadratic in the floor) at cut-out cost.
     """
     lib = _lib.load()
     if not torch.cuda.is_available():
@@ -196,11 +201,30 @@ def prepare_domain(frames, header, size=None, cut=None, origin=None, nbody=2, fl
     _lib.check(lib.lapf_frame_prep(fr.data_ptr(), nf, fy, fx, cut_t.data_ptr(), ny, nx,
                                    float(saturation_level(header)), float(read_noise(header)),
                                    data.data_ptr(), weight.data_ptr(), _stream_ptr(dev)))
+    outside = None
+    if whole_frame:
+        # full-array weight map through the same kernel, then all-minus-inside in FP64
+        zero = torch.zeros((nf, 2), dtype=torch.int32, device=dev)
+        d_all = torch.empty((nf, fy, fx), dtype=torch.float32, device=dev)
+        w_all = torch.empty_like(d_all)
+        _lib.check(lib.lapf_frame_prep(fr.data_ptr(), nf, fy, fx, zero.data_ptr(), fy, fx,
+                                       float(saturation_level(header)), float(read_noise(header)),
+                                       d_all.data_ptr(), w_all.data_ptr(), _stream_ptr(dev)))
+
+        def sums(d, w):
+            d64, w64 = d.double(), w.double()
+            return torch.stack([w64.sum(dim=(1, 2)), (w64 * d64).sum(dim=(1, 2)), (w64 * d64 * d64).sum(dim=(1, 2))], dim=1)
+
+        outside = sums(d_all, w_all) - sums(data, weight)
     if into is not None:
         into.origin.copy_(torch.as_tensor((org_np + cut_np).astype(np.int32)))
+        if outside is not None:
+            if into.outside is None:
+                raise ValueError("into was created without whole_frame=True")
+            into.outside.copy_(outside)
         return into
     return PixelDomain(data, weight, (org_np + cut_np).astype(np.int32), nbody=nbody,
-                       floor_index=floor_index, device=device)
+                       floor_index=floor_index, device=device, outside=outside)
 
 
 def initial_parameters(image, guess, nbody=2, origin=(0, 0)):

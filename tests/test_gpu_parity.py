@@ -334,3 +334,76 @@ def test_device_random_stream_equals_oracle_stream(gpu):
             assert z[i] == pytest.approx(zo, rel=1e-12, abs=1e-14)
             assert lnu[i] == pytest.approx(math.log(uo) if uo > 0 else -math.inf, rel=1e-13)
         assert set(k.tolist()) == set(range(npar))
+
+
+# ---------------------------------------------------------------------------------------------
+# whole-frame chi-square at stamp cost, and full-size consistency
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nbody,size", [(2, 64), (3, 128)])
+def test_whole_frame_domain_equals_reference_domain(gpu, nbody, size):
+    """The reference sums chi-square over the whole 1024 x 1024 frame (apf_step2.py:94,134-137).
+    Cut-out + exact sums of the outside pixels against the constant floor gives the same number."""
+    synth = gpu["synth"]
+    lay = orc.layout_for(nbody)
+    img, truth = synth.make_frame(4, nbody)
+    ox, oy = synth.stamp_origin(size)
+    full = gpu["frame"].prepare_domain(img, HEADER, nbody=nbody)                       # generic kernel
+    cut = gpu["frame"].prepare_domain(img, HEADER, size=size, cut=(ox, oy), nbody=nbody, whole_frame=True)
+    assert cut.outside is not None and tuple(cut.origin[0].tolist()) == (ox, oy)
+    vecs = np.vstack([truth.astype(np.float32).astype(np.float64)[None],
+                      _random_vectors(truth, nbody, 5, np.random.default_rng(3), spread=0.3)])
+    _, c_full = full.model_chi2(vecs)
+    _, c_cut = cut.model_chi2(vecs)
+    np.testing.assert_allclose(c_cut.cpu().numpy(), c_full.cpu().numpy(), rtol=1e-7)
+    img64 = img.astype(np.float64)
+    w = orc.weight_map(img64, HEADER)
+    for q, c in zip(vecs[:3], c_cut.cpu().numpy()):
+        ref = orc.chi_squared_weighted(img64, orc.model_image(q, lay, 1024, 1024), w)
+        assert c == pytest.approx(ref, rel=1e-7)
+
+
+def test_sampler_on_whole_frame_domain_replays_full_frame_oracle(gpu):
+    """The sampler with the outside sums follows the oracle run on the FULL frame, i.e. the
+    reference's own pixel domain, update by update."""
+    synth = gpu["synth"]
+    lay = orc.layout_for(2)
+    img, truth = synth.make_frame(0, 2)
+    ox, oy = synth.stamp_origin(64)
+    dom = gpu["frame"].prepare_domain(img, HEADER, size=64, cut=(ox, oy), nbody=2, whole_frame=True)
+    guess = synth.step1_guess(img, 2, sky_xy=(100, 120))
+    p0 = gpu["frame"].initial_parameters(img, guess, 2)
+    n_upd = 48
+    with gpu["sampler"].GibbsSampler(dom, p0[None], seed=99) as s:
+        chain = s.run(n_upd).cpu().numpy()[:, 0, :]
+    img64 = img.astype(np.float64)
+    res = orc.run_chain(img64, orc.weight_map(img64, HEADER), lay, p0, orc.PhiloxStream(99, 0, 16),
+                        n_updates=n_upd, burn_in=0)
+    np.testing.assert_allclose(chain[:, :-1], res.rows[1:, :-1], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(chain[:, -1], res.rows[1:, -1], rtol=1e-7)
+    assert res.accepts.sum() > 5
+
+
+def test_full_size_batch_state_is_consistent_with_k1(gpu):
+    """BASELINE configs[2] at full size (65,536 walkers x 100 epochs): after a run, the chi-square
+    every walker carries equals the stateless operator applied to its parameters -- bit for bit --
+    every update was counted once, and the batch statistics add up."""
+    torch = gpu["torch"]
+    synth = gpu["synth"]
+    W, F, S = 65536, 100, 64
+    stamps, origins = synth.make_stamps(F, S)
+    dom = gpu["frame"].prepare_domain(stamps, HEADER, origin=origins, nbody=2)
+    frame_of = (np.arange(W) % F).astype(np.int32)
+    p_frame = np.array([synth.truth_parameters(2, f) for f in range(F)])
+    with gpu["sampler"].GibbsSampler(dom, p_frame[frame_of], frame_of, seed=31, burn_in=0, thin=16) as s:
+        chain = s.run(48)
+        st, tries, acc = s.state()
+        stats = s.stats()
+    assert chain.shape == (3, W, 17)
+    assert torch.equal(chain[-1], st)                                     # last recorded row = final state
+    _, chi = dom.model_chi2(st[:, :16], frame_of=frame_of)
+    assert torch.equal(chi, st[:, 16])                                    # K1 == K2, bitwise
+    assert bool((tries.sum(dim=1) == 48).all()) and bool((acc <= tries).all())
+    assert int(stats["tries"].sum()) == 48 * W
+    assert stats["walkers_per_frame"].cpu().numpy().tolist() == np.bincount(frame_of, minlength=F).tolist()
+    # chi-square per pixel of chains started at the in-model truth stays of order one
+    assert 0.8 < float(st[:, 16].median()) / (S * S) < 1.3
