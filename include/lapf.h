@@ -37,6 +37,9 @@ extern "C" {
 
 #define LAPF_ABI_VERSION 1
 #define LAPF_MAX_PARAMS 19
+/* lapf_problem.flags: evaluate every component at every pixel, also where its value is provably
+ * below 2^-24 of the floor (default: such far-field rows are skipped; results agree to FP32 rounding) */
+#define LAPF_FLAG_NO_CULL 1
 
 typedef enum lapf_status {
     LAPF_OK = 0,
@@ -56,7 +59,7 @@ typedef struct lapf_problem {
     int32_t floor_index;    /* parameter slot added as the constant floor: 12 reproduces the
                                reference for both layouts (apf_step2.py:120 -- sigmax2 --
                                and 3body/apf_step2_3body.py:121 -- bkgd) */
-    int32_t reserved;
+    int32_t flags;          /* 0, or LAPF_FLAG_NO_CULL */
     const float* data;      /* device [F][ny][nx]; finite everywhere (0 on masked pixels) */
     const float* weight;    /* device [F][ny][nx] */
     const int32_t* origin;  /* device [F][2]: frame coordinates (x0, y0) of pixel [0][0] */

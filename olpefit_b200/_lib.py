@@ -16,7 +16,7 @@ class LapfError(RuntimeError):
 
 class Problem(C.Structure):
     _fields_ = [("nbody", C.c_int32), ("ny", C.c_int32), ("nx", C.c_int32), ("n_frames", C.c_int32),
-                ("floor_index", C.c_int32), ("reserved", C.c_int32),
+                ("floor_index", C.c_int32), ("flags", C.c_int32),
                 ("data", C.c_void_p), ("weight", C.c_void_p), ("origin", C.c_void_p),
                 ("outside", C.c_void_p)]
 

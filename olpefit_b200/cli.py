@@ -35,8 +35,8 @@ def _parser(kind):
     else:
         ap.add_argument("--n-steps", type=int, default=5000)
     ap.add_argument("--burn-in", type=int, default=None)
-    ap.add_argument("--stamp", type=int, default=64, choices=[32, 64, 128],
-                    help="side of the square pixel domain centred on the objects")
+    ap.add_argument("--stamp", type=int, default=128, choices=[32, 64, 128],
+                    help="side of the square cut-out, centred on the objects, in which the Gaussians are evaluated")
     ap.add_argument("--domain", choices=["frame", "stamp"], default="frame",
                     help="frame: chi-square over the whole image like the reference (pixels outside the stamp enter "
                          "through their exact sums against the constant floor); stamp: the cut-out only")

@@ -83,6 +83,7 @@ struct ProbPtrs {
     const int32_t* origin;
     const double* outside;   // [F][3] or nullptr (see lapf_problem.outside)
     int n_frames, floor_index;
+    int cull;                // far-field culling on/off
 };
 
 // chi-square of the image pixels outside the cut-out, where the model is the constant floor f
@@ -114,6 +115,7 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
     load_shape<NB>(cf, 1, tf[warp]);
     __shared__ __align__(16) float rt[4][NY * 4 * NB];
     build_row_table<NB, NY>(rt[warp], cf, lane);
+    if (pr.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB>(cf);
     const size_t off = (size_t)f * NX * NY;
     double chi = warp_chi2<NB, NX, NY, STORE, false>(cf, rt[warp], pr.data + off, pr.weight + off,
                                                            STORE ? model_out + (size_t)b * NX * NY : nullptr, lane);
@@ -243,7 +245,7 @@ struct RunArgs {
     uint64_t seed;
     double widths[LAPF_MAX_PARAMS];
     uint32_t log_mask;
-    int thin, floor_index, n_items;
+    int thin, floor_index, n_items, cull;
 };
 
 // One walker for n_updates updates.  TEAM = 1: one warp does everything.  TEAM > 1 (few walkers,
@@ -309,6 +311,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         const int which = (k == L::I_SX2 || k == L::I_SY2 || k == L::I_TH2) ? 1 : 0;
         if (shape_moved) load_shape<NB>(cf, which, ws.tf);
         build_row_table<NB, NY>(rt, cf, lane);
+        if (a.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB>(cf);
         double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw);   // :314-316
         if (TEAM > 1) {
             double* slot_p = team_part + (u & 1) * TEAM;       // double-buffered: one barrier per update
@@ -581,6 +584,14 @@ struct lapf_sampler {
     int32_t* item_count = nullptr;
 };
 
+// Far-field culling (set_cull) is on unless the caller sets bit 0 of lapf_problem.flags or the
+// environment variable LAPF_NO_CULL is set; 32-pixel stamps have no far field worth the test.
+static int cull_enabled(const lapf_problem* p) {
+    if (p->flags & LAPF_FLAG_NO_CULL) return 0;
+    if (getenv("LAPF_NO_CULL")) return 0;
+    return p->nx >= 64 ? 1 : 0;
+}
+
 static bool stamp_supported(int ny, int nx) { return ny == nx && (nx == 32 || nx == 64 || nx == 128); }
 
 static int check_problem(const lapf_problem* p) {
@@ -669,7 +680,8 @@ int lapf_model_chi2(const lapf_problem* prob, const double* params, int64_t B, c
     if (B == 0) return LAPF_OK;
     if ((rc = require_device())) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    ProbPtrs pr{prob->data, prob->weight, prob->origin, prob->outside, prob->n_frames, prob->floor_index};
+    ProbPtrs pr{prob->data, prob->weight, prob->origin, prob->outside, prob->n_frames, prob->floor_index,
+                cull_enabled(prob)};
     if (stamp_supported(prob->ny, prob->nx) && (!model_out || ((uintptr_t)model_out & 15) == 0)) {
         if (prob->nbody == 2)
             launch_stamp_k1_size<2>(prob->nx, model_out != nullptr, pr, params, B, frame_of, model_out, chi2_out, st);
@@ -913,6 +925,7 @@ int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int6
     memcpy(a.widths, s->widths, sizeof(a.widths));
     a.log_mask = s->log_mask;
     a.thin = s->cfg.thin; a.floor_index = pb.floor_index; a.n_items = s->n_items;
+    a.cull = cull_enabled(&pb);
     int rc = launch_dispatch(s, a, (cudaStream_t)stream);
     if (rc) return rc;
     s->count += n_updates;

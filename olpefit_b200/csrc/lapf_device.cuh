@@ -107,6 +107,8 @@ struct Coef {
     float x0[K], y0[K], amp[K];   // component 2o = narrow core of object o, 2o+1 = its wide wing
     float sa[2], sb[2], sc[2];    // shape 0 = narrow, 1 = wide; a, b, c of A.1 times -log2(e)
     float floor;
+    uint32_t rowmask[K];          // bit i: component k can matter in row step i (set_cull)
+    uint32_t panmask[K];          // bit p: component k can matter in column panel p
 };
 
 // a, b, c of astropy Gaussian2D.evaluate, pre-scaled so that the
@@ -219,6 +221,61 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
     __syncwarp();
 }
 
+// Far-field culling.  |A_k| 2^(q) <= |A_k| 2^(kappa dy^2) for every pixel of a row at distance dy
+// from the component's centre (kappa = sc - sb^2/(4 sa), the exponent maximised over dx), and the
+// same with the roles of x and y swapped for a column panel.  A component whose bound over a whole
+// row step (or panel) is below tau = 2^-24 |floor| cannot change the FP32 model value there -- the
+// model is at least of the size of the floor -- so that step skips it: no MUFU, no FFMA.  On a
+// 128-pixel stamp the narrow cores matter in ~1/8 of the pixels and the wide wings in ~2/3.
+// The decision is a pure function of the coefficients (chi-square stays a function of the
+// parameter vector); any nan/inf in them disables culling so the nan reaches chi-square.
+template <int NB, int NX, int NY>
+__device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
+    using G = Geo<NX>;
+    constexpr int K = 2 * NB;
+    constexpr int STEPS = NY / G::RG;
+    constexpr uint32_t kAllRows = STEPS >= 32 ? 0xffffffffu : ((1u << STEPS) - 1u);
+    constexpr uint32_t kAllPans = (1u << G::PANELS) - 1u;
+    // lane k < K works out component k, then everybody fetches the result
+    float a = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k)
+        if (lane == k) { a = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
+    const int sh = lane & 1;
+    const float sa = sh ? cf.sa[1] : cf.sa[0], sb = sh ? cf.sb[1] : cf.sb[0], sc = sh ? cf.sc[1] : cf.sc[0];
+    const float tau = 0x1p-24f * fabsf(cf.floor);
+    const float L = log2f(fabsf(a) / tau);                 // bits of headroom above tau
+    uint32_t rm = kAllRows, pm = kAllPans;
+    if (L <= 0.f) {
+        rm = 0u; pm = 0u;                                  // below tau everywhere
+    } else {
+        const float ky = sc - sb * sb / (4.f * sa), kx = sa - sb * sb / (4.f * sc);   // both < 0
+        const float Y = sqrtf(L / -ky) + 1.f, X = sqrtf(L / -kx) + 1.f;              // + one pixel of slack
+        if (Y < 1e6f && fabsf(y0) < 1e6f) {                // false for nan / inf: keep everything
+            const int lo = max(0, (int)ceilf((y0 - Y - (float)(G::RG - 1)) / (float)G::RG));
+            const int hi = min(STEPS - 1, (int)floorf((y0 + Y) / (float)G::RG));
+            rm = (lo <= hi) ? ((kAllRows >> (STEPS - 1 - hi + lo)) << lo) : 0u;
+        }
+        if (X < 1e6f && fabsf(x0) < 1e6f) {
+            pm = 0u;
+#pragma unroll
+            for (int p = 0; p < G::PANELS; ++p)
+                if (x0 + X >= (float)(p * G::PW) && x0 - X <= (float)(p * G::PW + G::PW - 1)) pm |= 1u << p;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        cf.rowmask[k] = __shfl_sync(kFull, rm, k);
+        cf.panmask[k] = __shfl_sync(kFull, pm, k);
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void no_cull(Coef<NB>& cf) {
+#pragma unroll
+    for (int k = 0; k < 2 * NB; ++k) { cf.rowmask[k] = 0xffffffffu; cf.panmask[k] = 0xffffffffu; }
+}
+
 // PREP = true: the planes already hold  d*sqrt(w)  and  -sqrt(w)  (the sampler converts a stamp
 // once after staging it); PREP = false: raw data / weight planes, converted per pixel.  Both give
 // bit-identical chi-square: the residual is always  r = fma(-sqrt(w), m, d*sqrt(w)),  chi2 += r*r.
@@ -248,6 +305,13 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
     for (int pan = 0; pan < G::PANELS; ++pan) {
         const int colA = pan * G::PW + 4 * c + (G::PW / 2) * swap;
         const int colB = pan * G::PW + 4 * c + (G::PW / 2) * (1 - swap);
+        // Row-step masks of this panel per shape class (narrow cores = even k, wide wings = odd k):
+        // a class is evaluated in a step if any of its components can matter there.  Class
+        // granularity keeps each evaluated block large enough to interleave (NB x 4 independent
+        // chains per pixel pair group).
+        uint32_t mcls[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < K; ++k) mcls[k & 1] |= ((cf.panmask[k] >> pan) & 1u) ? cf.rowmask[k] : 0u;
         float2 xd[K][4];   // pixel pairs: (0,1) (2,3) of group A, (0,1) (2,3) of group B
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -281,8 +345,9 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
                 float2 m[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) m[j] = make_float2(cf.floor, cf.floor);
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
+                const uint32_t bit = 1u << (ib + ii);
+                const bool on0 = (mcls[0] & bit) != 0u, on1 = (mcls[1] & bit) != 0u;
+                auto add_component = [&](int k) {
                     const float2 sa2 = make_float2(cf.sa[k & 1], cf.sa[k & 1]);
                     const float2 by2 = make_float2(rc[k], rc[k]);
                     const float2 cy2 = make_float2(rc[K + k], rc[K + k]);
@@ -294,6 +359,16 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
                         const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
                         m[j] = __ffma2_rn(am2, e, m[j]);
                     }
+                };
+                if (on0 && on1) {          // near field: everything, one fully interleaved block
+#pragma unroll
+                    for (int k = 0; k < K; ++k) add_component(k);
+                } else if (on1) {          // wings only
+#pragma unroll
+                    for (int k = 1; k < K; k += 2) add_component(k);
+                } else if (on0) {          // cores only (a core outliving its wing: unusual)
+#pragma unroll
+                    for (int k = 0; k < K; k += 2) add_component(k);
                 }
                 if (STORE) {
                     *reinterpret_cast<float4*>(mp + colA) = make_float4(m[0].x, m[0].y, m[1].x, m[1].y);

@@ -24,7 +24,8 @@ class PixelDomain:
     """F frames of ny x nx pixels resident in HBM: data, weight (= 1/err^2, 0 where masked) and
     the frame coordinates of pixel [0][0] of each frame."""
 
-    def __init__(self, data, weight, origin=None, nbody=2, floor_index=None, device="cuda", outside=None):
+    def __init__(self, data, weight, origin=None, nbody=2, floor_index=None, device="cuda", outside=None,
+                 cull=True):
         _lib.load()
         if not torch.cuda.is_available():
             raise _lib.LapfError("no CUDA device: olpefit_b200 has no CPU path")
@@ -45,6 +46,7 @@ class PixelDomain:
         self.nbody = int(nbody)
         self.nparam = layout.nparam(self.nbody)
         self.floor_index = layout.REFERENCE_FLOOR_INDEX if floor_index is None else int(floor_index)
+        self.flags = 0 if cull else 1          # LAPF_FLAG_NO_CULL
         # optional [F, 3] float64: sum w, sum w d, sum w d^2 over the image pixels outside the cut-outs
         self.outside = None
         if outside is not None:
@@ -52,7 +54,7 @@ class PixelDomain:
             self.outside = o.to(self.device, torch.float64).reshape(self.n_frames, 3).contiguous()
 
     def problem(self) -> _lib.Problem:
-        return _lib.Problem(self.nbody, self.ny, self.nx, self.n_frames, self.floor_index, 0,
+        return _lib.Problem(self.nbody, self.ny, self.nx, self.n_frames, self.floor_index, self.flags,
                             self.data.data_ptr(), self.weight.data_ptr(), self.origin.data_ptr(),
                             self.outside.data_ptr() if self.outside is not None else None)
 
