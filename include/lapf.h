@@ -135,8 +135,10 @@ int lapf_sampler_state(lapf_sampler* s, double* state_out, uint32_t* tries_out,
                        uint32_t* accepts_out, void* stream);
 
 /* K4 -- batch statistics, written to device memory:
- *   totals_out  device int64[2P+1]: sum over walkers of tries[P], accepts[P], then the minimum
- *               over walkers and parameters of tries (stop rule of apf_step2.py:300, globalised)
+ *   totals_out  device int64[2P+2]: sum over walkers of tries[P], accepts[P], then the minimum
+ *               over walkers and parameters of tries (stop rule of apf_step2.py:300, globalised),
+ *               then the number of exponentials the sampler really evaluated so far (what is
+ *               left of ny*nx*K per update after far-field culling; roofline accounting)
  *   moments_out device double[F][P+1][3] or NULL: per frame and column, over that frame's
  *               walkers: sum of chain means, sum of squared chain means, sum of chain variances
  *               of the rows recorded so far (the ingredients of apf_step3.py:265-276)

@@ -115,7 +115,7 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
     load_shape<NB>(cf, 1, tf[warp]);
     __shared__ __align__(16) float rt[4][NY * 4 * NB];
     build_row_table<NB, NY>(rt[warp], cf, lane);
-    if (pr.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB>(cf);
+    if (pr.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
     const size_t off = (size_t)f * NX * NY;
     double chi = warp_chi2<NB, NX, NY, STORE, false>(cf, rt[warp], pr.data + off, pr.weight + off,
                                                            STORE ? model_out + (size_t)b * NX * NY : nullptr, lane);
@@ -237,6 +237,7 @@ struct RunArgs {
     double* moments;             // [W][P+1][2] running sum / sum of squares of recorded rows
     uint32_t* tries;             // [W][P]
     uint32_t* accepts;           // [W][P]
+    unsigned long long* exps;    // [W] exponentials actually evaluated (after far-field culling)
     double* chain;               // [rows][W][P+1] or nullptr
     int64_t n_walkers;
     int64_t t0, n_updates;       // first update index, updates in this launch
@@ -278,6 +279,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
 
     int64_t next_rec = a.next_record;
     int64_t row = 0;
+    unsigned long long n_exps = 0;
 
 #pragma unroll 1
     for (int64_t u = 0; u < a.n_updates; ++u) {
@@ -311,8 +313,10 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         const int which = (k == L::I_SX2 || k == L::I_SY2 || k == L::I_TH2) ? 1 : 0;
         if (shape_moved) load_shape<NB>(cf, which, ws.tf);
         build_row_table<NB, NY>(rt, cf, lane);
-        if (a.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB>(cf);
-        double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw);   // :314-316
+        if (a.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
+        unsigned e_upd = 0;
+        double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw, &e_upd);   // :314-316
+        n_exps += e_upd;
         if (TEAM > 1) {
             double* slot_p = team_part + (u & 1) * TEAM;       // double-buffered: one barrier per update
             if (lane == 0) slot_p[tw] = chi_t;
@@ -354,6 +358,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
     if (tw == 0) {
         if (lane < P) st[lane] = p;
         if (lane == P) st[P] = chi_c;
+        if (lane == 0) a.exps[wl] += n_exps;
     }
 }
 
@@ -417,31 +422,35 @@ __global__ void pack_state_kernel(const double* __restrict__ init, const double*
 // K4: batch statistics
 // =============================================================================================
 __global__ void totals_kernel(const uint32_t* __restrict__ tries, const uint32_t* __restrict__ accepts,
-                              int P, int64_t W, unsigned long long* __restrict__ out /*[2P+1]*/) {
+                              const unsigned long long* __restrict__ exps, int P, int64_t W,
+                              unsigned long long* __restrict__ out /*[2P+2]*/) {
     // integer sums and a min: order-independent, so atomics are deterministic here
     const int j = blockIdx.y;
-    unsigned long long st = 0, sa = 0, mn = ~0ull;
+    unsigned long long st = 0, sa = 0, mn = ~0ull, se = 0;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += (int64_t)gridDim.x * blockDim.x) {
         const unsigned long long t = tries[w * P + j];
         st += t;
         sa += accepts[w * P + j];
         mn = min(mn, t);
+        if (j == 0) se += exps[w];
     }
     for (int off = 16; off >= 1; off >>= 1) {
         st += __shfl_xor_sync(kFull, st, off);
         sa += __shfl_xor_sync(kFull, sa, off);
         mn = min(mn, __shfl_xor_sync(kFull, mn, off));
+        se += __shfl_xor_sync(kFull, se, off);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(out + j, st);
         atomicAdd(out + P + j, sa);
         atomicMin(out + 2 * P, mn);
+        if (j == 0) atomicAdd(out + 2 * P + 1, se);
     }
 }
 
 __global__ void totals_init_kernel(unsigned long long* out, int P) {
     const int i = threadIdx.x;
-    if (i < 2 * P) out[i] = 0ull;
+    if (i < 2 * P || i == 2 * P + 1) out[i] = 0ull;
     if (i == 2 * P) out[i] = ~0ull;
 }
 
@@ -577,6 +586,7 @@ struct lapf_sampler {
     double* moments = nullptr;
     uint32_t* tries = nullptr;
     uint32_t* accepts = nullptr;
+    unsigned long long* exps = nullptr;
     int32_t* walker_of = nullptr;
     int32_t* frame_start = nullptr;
     int32_t* item_frame = nullptr;
@@ -764,7 +774,7 @@ static int launch_dispatch(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
 
 static void free_sampler(lapf_sampler* s) {
     if (!s) return;
-    cudaFree(s->state); cudaFree(s->shift); cudaFree(s->moments); cudaFree(s->tries); cudaFree(s->accepts);
+    cudaFree(s->state); cudaFree(s->shift); cudaFree(s->moments); cudaFree(s->tries); cudaFree(s->accepts); cudaFree(s->exps);
     cudaFree(s->walker_of); cudaFree(s->frame_start); cudaFree(s->item_frame); cudaFree(s->item_first);
     cudaFree(s->item_count);
     delete s;
@@ -846,6 +856,7 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     CUS(cudaMalloc((void**)&s->moments, sizeof(double) * nst * 2));
     CUS(cudaMalloc((void**)&s->tries, sizeof(uint32_t) * W * P));
     CUS(cudaMalloc((void**)&s->accepts, sizeof(uint32_t) * W * P));
+    CUS(cudaMalloc((void**)&s->exps, sizeof(unsigned long long) * W));
     CUS(cudaMalloc((void**)&s->walker_of, sizeof(int32_t) * W));
     CUS(cudaMalloc((void**)&s->frame_start, sizeof(int32_t) * (F + 1)));
     CUS(cudaMalloc((void**)&s->item_frame, sizeof(int32_t) * s->n_items));
@@ -874,6 +885,7 @@ int lapf_sampler_reset(lapf_sampler* s, const double* init_params, uint64_t seed
     CU(cudaMemsetAsync(s->moments, 0, sizeof(double) * nst * 2, st));
     CU(cudaMemsetAsync(s->tries, 0, sizeof(uint32_t) * W * P, st));
     CU(cudaMemsetAsync(s->accepts, 0, sizeof(uint32_t) * W * P, st));
+    CU(cudaMemsetAsync(s->exps, 0, sizeof(unsigned long long) * W, st));
     // initial chi-square (apf_step2.py:283-289) through K1, then pack the state
     double* chi0 = nullptr;
     CU(cudaMallocAsync((void**)&chi0, sizeof(double) * W, st));
@@ -915,7 +927,7 @@ int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int6
     a.item_frame = s->item_frame; a.item_first = s->item_first; a.item_count = s->item_count;
     a.walker_of = s->walker_of;
     a.state = s->state; a.shift = s->shift; a.moments = s->moments;
-    a.tries = s->tries; a.accepts = s->accepts;
+    a.tries = s->tries; a.accepts = s->accepts; a.exps = s->exps;
     a.chain = chain_out;
     a.n_walkers = s->cfg.n_walkers;
     a.t0 = s->count; a.n_updates = n_updates;
@@ -952,7 +964,7 @@ int lapf_sampler_stats(lapf_sampler* s, int64_t* totals_out, double* moments_out
     if (totals_out) {
         totals_init_kernel<<<1, 64, 0, st>>>((unsigned long long*)totals_out, P);
         const unsigned gx = (unsigned)std::min<int64_t>(148, (W + 255) / 256);
-        totals_kernel<<<dim3(gx, P), 256, 0, st>>>(s->tries, s->accepts, P, W, (unsigned long long*)totals_out);
+        totals_kernel<<<dim3(gx, P), 256, 0, st>>>(s->tries, s->accepts, s->exps, P, W, (unsigned long long*)totals_out);
         CU(cudaGetLastError());
         s->launches += 2;
     }

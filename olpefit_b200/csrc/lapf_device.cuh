@@ -107,8 +107,10 @@ struct Coef {
     float x0[K], y0[K], amp[K];   // component 2o = narrow core of object o, 2o+1 = its wide wing
     float sa[2], sb[2], sc[2];    // shape 0 = narrow, 1 = wide; a, b, c of A.1 times -log2(e)
     float floor;
-    uint32_t rowmask[K];          // bit i: component k can matter in row step i (set_cull)
-    uint32_t panmask[K];          // bit p: component k can matter in column panel p
+    // far-field culling (set_cull): row steps [lo, hi] in which a class of components can matter
+    // (class 0 = narrow cores, 1 = wide wings; empty when lo > hi), and the column panels (bit p)
+    int lo[2], hi[2];
+    uint32_t pan[2];
 };
 
 // a, b, c of astropy Gaussian2D.evaluate, pre-scaled so that the
@@ -225,18 +227,19 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
 // from the component's centre (kappa = sc - sb^2/(4 sa), the exponent maximised over dx), and the
 // same with the roles of x and y swapped for a column panel.  A component whose bound over a whole
 // row step (or panel) is below tau = 2^-24 |floor| cannot change the FP32 model value there -- the
-// model is at least of the size of the floor -- so that step skips it: no MUFU, no FFMA.  On a
-// 128-pixel stamp the narrow cores matter in ~1/8 of the pixels and the wide wings in ~2/3.
-// The decision is a pure function of the coefficients (chi-square stays a function of the
-// parameter vector); any nan/inf in them disables culling so the nan reaches chi-square.
+// model is at least of the size of the floor -- so those rows skip it: no MUFU, no FFMA.  Rows are
+// culled per CLASS (all narrow cores / all wide wings): the active rows of a class are one interval
+// of row steps, so a panel is walked as at most five segments (none, wings, all, wings, none), each
+// a tight loop without per-row tests.  On a 128-pixel stamp the cores matter in ~1/4 of the rows and
+// the wings in ~2/3.  The decision is a pure function of the coefficients (chi-square stays a
+// function of the parameter vector); a nan/inf in them disables culling so it reaches chi-square.
 template <int NB, int NX, int NY>
 __device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
     using G = Geo<NX>;
     constexpr int K = 2 * NB;
     constexpr int STEPS = NY / G::RG;
-    constexpr uint32_t kAllRows = STEPS >= 32 ? 0xffffffffu : ((1u << STEPS) - 1u);
     constexpr uint32_t kAllPans = (1u << G::PANELS) - 1u;
-    // lane k < K works out component k, then everybody fetches the result
+    // lane k < K works out component k; lanes >= K hold the neutral element
     float a = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
 #pragma unroll
     for (int k = 1; k < K; ++k)
@@ -245,16 +248,17 @@ __device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
     const float sa = sh ? cf.sa[1] : cf.sa[0], sb = sh ? cf.sb[1] : cf.sb[0], sc = sh ? cf.sc[1] : cf.sc[0];
     const float tau = 0x1p-24f * fabsf(cf.floor);
     const float L = log2f(fabsf(a) / tau);                 // bits of headroom above tau
-    uint32_t rm = kAllRows, pm = kAllPans;
-    if (L <= 0.f) {
-        rm = 0u; pm = 0u;                                  // below tau everywhere
+    int lo = 0, hi = STEPS - 1;                            // default: everything (also for nan / inf)
+    uint32_t pm = kAllPans;
+    if (L <= 0.f) {                                        // below tau everywhere
+        lo = STEPS; hi = -1; pm = 0u;
     } else {
         const float ky = sc - sb * sb / (4.f * sa), kx = sa - sb * sb / (4.f * sc);   // both < 0
         const float Y = sqrtf(L / -ky) + 1.f, X = sqrtf(L / -kx) + 1.f;              // + one pixel of slack
-        if (Y < 1e6f && fabsf(y0) < 1e6f) {                // false for nan / inf: keep everything
-            const int lo = max(0, (int)ceilf((y0 - Y - (float)(G::RG - 1)) / (float)G::RG));
-            const int hi = min(STEPS - 1, (int)floorf((y0 + Y) / (float)G::RG));
-            rm = (lo <= hi) ? ((kAllRows >> (STEPS - 1 - hi + lo)) << lo) : 0u;
+        if (Y < 1e6f && fabsf(y0) < 1e6f) {
+            lo = max(0, (int)ceilf((y0 - Y - (float)(G::RG - 1)) / (float)G::RG));
+            hi = min(STEPS - 1, (int)floorf((y0 + Y) / (float)G::RG));
+            if (lo > hi) { lo = STEPS; hi = -1; }
         }
         if (X < 1e6f && fabsf(x0) < 1e6f) {
             pm = 0u;
@@ -263,20 +267,31 @@ __device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
                 if (x0 + X >= (float)(p * G::PW) && x0 - X <= (float)(p * G::PW + G::PW - 1)) pm |= 1u << p;
         }
     }
+    if (lane >= K) { lo = STEPS; hi = -1; pm = 0u; }
+    // hull over the components of each class: lanes of equal parity (xor 2, 4 keeps the parity)
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        cf.rowmask[k] = __shfl_sync(kFull, rm, k);
-        cf.panmask[k] = __shfl_sync(kFull, pm, k);
+    for (int off = 2; off <= 4; off <<= 1) {
+        lo = min(lo, __shfl_xor_sync(kFull, lo, off));
+        hi = max(hi, __shfl_xor_sync(kFull, hi, off));
+        pm |= __shfl_xor_sync(kFull, pm, off);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        cf.lo[c] = __shfl_sync(kFull, lo, c);
+        cf.hi[c] = __shfl_sync(kFull, hi, c);
+        cf.pan[c] = __shfl_sync(kFull, pm, c);
     }
 }
 
-template <int NB>
+template <int NB, int NX, int NY>
 __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
 #pragma unroll
-    for (int k = 0; k < 2 * NB; ++k) { cf.rowmask[k] = 0xffffffffu; cf.panmask[k] = 0xffffffffu; }
+    for (int c = 0; c < 2; ++c) { cf.lo[c] = 0; cf.hi[c] = NY / Geo<NX>::RG - 1; cf.pan[c] = 0xffffffffu; }
 }
 
-// PREP = true: the planes already hold  d*sqrt(w)  and  -sqrt(w)  (the sampler converts a stamp
+// Row steps [i0, i1) of one panel for the component classes KIND says (0: none, the model is the
+// floor; 1: wide wings only; 2: all components).  Returns the FP32-accumulated chi-square of these
+// rows as FP64.  PREP = true: the planes hold d*sqrt(w) and -sqrt(w) (the sampler converts a stamp
 // once after staging it); PREP = false: raw data / weight planes, converted per pixel.  Both give
 // bit-identical chi-square: the residual is always  r = fma(-sqrt(w), m, d*sqrt(w)),  chi2 += r*r.
 //
@@ -284,20 +299,98 @@ __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
 // instruction, scalar coefficients as broadcast operands.  Per pixel PAIR and component that is
 // 3 FFMA2 + 2 MUFU.EX2, which keeps the issue slots needed per MUFU below the SFU's own rate
 // (measured: a MUFU costs ~4 issue cycles), so the loop is SFU-bound.
-//
-// TEAM > 1: TEAM warps share one parameter vector; warp `tw` of the team takes every TEAM-th row
-// step and returns ITS partial sum (the caller combines the partials in a fixed order).
+template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM, int KIND>
+__device__ __forceinline__ double row_steps(const Coef<NB>& cf, const float2 (&xd)[2 * NB][4], int i0, int i1,
+                                            int tw, int g, int colA, int colB, const float* __restrict__ rt,
+                                            const float* __restrict__ d, const float* __restrict__ w,
+                                            float* __restrict__ model_out) {
+    using G = Geo<NX>;
+    constexpr int K = 2 * NB;
+    // first step >= i0 that belongs to warp tw of the team
+    int i = i0 + ((tw - i0) % TEAM + TEAM) % TEAM;
+    if (i >= i1) return 0.0;
+    const int r0 = i * G::RG + g;
+    const float* rp = rt + r0 * 2 * K;
+    const float* dp = d + r0 * NX;
+    const float* wp = w + r0 * NX;
+    float* mp = STORE ? model_out + r0 * NX : nullptr;
+    float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (; i < i1; i += TEAM) {
+        const float4 dA = *reinterpret_cast<const float4*>(dp + colA);
+        const float4 dB = *reinterpret_cast<const float4*>(dp + colB);
+        const float4 wA = *reinterpret_cast<const float4*>(wp + colA);
+        const float4 wB = *reinterpret_cast<const float4*>(wp + colB);
+        float2 m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = make_float2(cf.floor, cf.floor);
+        if (KIND > 0) {
+            float rc[2 * K];
+#pragma unroll
+            for (int q = 0; q < 2 * K / 4; ++q) {
+                const float4 t4 = reinterpret_cast<const float4*>(rp)[q];
+                rc[4 * q] = t4.x; rc[4 * q + 1] = t4.y; rc[4 * q + 2] = t4.z; rc[4 * q + 3] = t4.w;
+            }
+#pragma unroll
+            for (int k = (KIND == 2 ? 0 : 1); k < K; k += (KIND == 2 ? 1 : 2)) {
+                const float2 sa2 = make_float2(cf.sa[k & 1], cf.sa[k & 1]);
+                const float2 by2 = make_float2(rc[k], rc[k]);
+                const float2 cy2 = make_float2(rc[K + k], rc[K + k]);
+                const float2 am2 = make_float2(cf.amp[k], cf.amp[k]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 t = __ffma2_rn(sa2, xd[k][j], by2);
+                    const float2 q = __ffma2_rn(xd[k][j], t, cy2);
+                    const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
+                    m[j] = __ffma2_rn(am2, e, m[j]);
+                }
+            }
+        }
+        if (STORE) {
+            *reinterpret_cast<float4*>(mp + colA) = make_float4(m[0].x, m[0].y, m[1].x, m[1].y);
+            *reinterpret_cast<float4*>(mp + colB) = make_float4(m[2].x, m[2].y, m[3].x, m[3].y);
+            mp += TEAM * G::RG * NX;
+        }
+        float2 dv[4] = {make_float2(dA.x, dA.y), make_float2(dA.z, dA.w), make_float2(dB.x, dB.y),
+                        make_float2(dB.z, dB.w)};
+        float2 wv[4] = {make_float2(wA.x, wA.y), make_float2(wA.z, wA.w), make_float2(wB.x, wB.y),
+                        make_float2(wB.z, wB.w)};
+        if (!PREP) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float rx = sqrtf(wv[j].x), ry = sqrtf(wv[j].y);
+                dv[j] = make_float2(dv[j].x * rx, dv[j].y * ry);
+                wv[j] = make_float2(-rx, -ry);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float2 ra = __ffma2_rn(wv[j], m[j], dv[j]);
+            const float2 rb = __ffma2_rn(wv[2 + j], m[2 + j], dv[2 + j]);
+            s0 = __ffma2_rn(ra, ra, s0);
+            s1 = __ffma2_rn(rb, rb, s1);
+        }
+        rp += TEAM * G::RG * 2 * K;
+        dp += TEAM * G::RG * NX;
+        wp += TEAM * G::RG * NX;
+    }
+    // FP32 partial sums of one segment (at most NY/RG steps x 8 pixels over 4 accumulators)
+    return (double)((s0.x + s0.y) + (s1.x + s1.y));
+}
+
+// chi-square of one parameter vector over the stamp by ONE warp (TEAM = 1), or this warp's share
+// of it (TEAM > 1: warp `tw` takes every TEAM-th row step; the caller adds the partials in a fixed
+// order).
 template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1>
 __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __restrict__ rt,
                                             const float* __restrict__ d, const float* __restrict__ w,
-                                            float* __restrict__ model_out, int lane, int tw = 0) {
+                                            float* __restrict__ model_out, int lane, int tw = 0,
+                                            unsigned* exps = nullptr) {
     using G = Geo<NX>;
     constexpr int K = 2 * NB;
     constexpr int STEPS = NY / G::RG;            // row steps per panel
-    // FP32 partials are folded into FP64 every FOLD steps
-    constexpr int FOLD = (TEAM == 1 && STEPS % 4 == 0) ? 4 : 1;
     static_assert(NY % G::RG == 0, "unsupported stamp height");
-    static_assert(STEPS % (TEAM * FOLD) == 0, "team size must divide the row steps");
+    static_assert(STEPS % TEAM == 0, "team size must divide the row steps");
     const int c = lane % G::LPR, g = lane / G::LPR;
     const int swap = (G::PW == 32) ? (g & 1) : 0;
     double acc = 0.0;
@@ -305,13 +398,6 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
     for (int pan = 0; pan < G::PANELS; ++pan) {
         const int colA = pan * G::PW + 4 * c + (G::PW / 2) * swap;
         const int colB = pan * G::PW + 4 * c + (G::PW / 2) * (1 - swap);
-        // Row-step masks of this panel per shape class (narrow cores = even k, wide wings = odd k):
-        // a class is evaluated in a step if any of its components can matter there.  Class
-        // granularity keeps each evaluated block large enough to interleave (NB x 4 independent
-        // chains per pixel pair group).
-        uint32_t mcls[2] = {0u, 0u};
-#pragma unroll
-        for (int k = 0; k < K; ++k) mcls[k & 1] |= ((cf.panmask[k] >> pan) & 1u) ? cf.rowmask[k] : 0u;
         float2 xd[K][4];   // pixel pairs: (0,1) (2,3) of group A, (0,1) (2,3) of group B
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -321,91 +407,21 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
                 xd[k][2 + jj] = make_float2((float)(colB + 2 * jj) - cf.x0[k], (float)(colB + 2 * jj + 1) - cf.x0[k]);
             }
         }
-        const int r0 = g + tw * FOLD * G::RG;    // first row of this warp
-        const float* rp = rt + r0 * 2 * K;
-        const float* dp = d + r0 * NX;
-        const float* wp = w + r0 * NX;
-        float* mp = STORE ? model_out + r0 * NX : nullptr;
-        constexpr int SKIP = (TEAM - 1) * FOLD * G::RG;   // rows that belong to the other warps of the team
-#pragma unroll 1
-        for (int ib = tw * FOLD; ib < STEPS; ib += TEAM * FOLD) {
-            float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
-#pragma unroll 1
-            for (int ii = 0; ii < FOLD; ++ii) {
-                float rc[2 * K];
-#pragma unroll
-                for (int q = 0; q < 2 * K / 4; ++q) {
-                    const float4 t4 = reinterpret_cast<const float4*>(rp)[q];
-                    rc[4 * q] = t4.x; rc[4 * q + 1] = t4.y; rc[4 * q + 2] = t4.z; rc[4 * q + 3] = t4.w;
-                }
-                const float4 dA = *reinterpret_cast<const float4*>(dp + colA);
-                const float4 dB = *reinterpret_cast<const float4*>(dp + colB);
-                const float4 wA = *reinterpret_cast<const float4*>(wp + colA);
-                const float4 wB = *reinterpret_cast<const float4*>(wp + colB);
-                float2 m[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) m[j] = make_float2(cf.floor, cf.floor);
-                const uint32_t bit = 1u << (ib + ii);
-                const bool on0 = (mcls[0] & bit) != 0u, on1 = (mcls[1] & bit) != 0u;
-                auto add_component = [&](int k) {
-                    const float2 sa2 = make_float2(cf.sa[k & 1], cf.sa[k & 1]);
-                    const float2 by2 = make_float2(rc[k], rc[k]);
-                    const float2 cy2 = make_float2(rc[K + k], rc[K + k]);
-                    const float2 am2 = make_float2(cf.amp[k], cf.amp[k]);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 t = __ffma2_rn(sa2, xd[k][j], by2);
-                        const float2 q = __ffma2_rn(xd[k][j], t, cy2);
-                        const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
-                        m[j] = __ffma2_rn(am2, e, m[j]);
-                    }
-                };
-                if (on0 && on1) {          // near field: everything, one fully interleaved block
-#pragma unroll
-                    for (int k = 0; k < K; ++k) add_component(k);
-                } else if (on1) {          // wings only
-#pragma unroll
-                    for (int k = 1; k < K; k += 2) add_component(k);
-                } else if (on0) {          // cores only (a core outliving its wing: unusual)
-#pragma unroll
-                    for (int k = 0; k < K; k += 2) add_component(k);
-                }
-                if (STORE) {
-                    *reinterpret_cast<float4*>(mp + colA) = make_float4(m[0].x, m[0].y, m[1].x, m[1].y);
-                    *reinterpret_cast<float4*>(mp + colB) = make_float4(m[2].x, m[2].y, m[3].x, m[3].y);
-                    mp += G::RG * NX;
-                }
-                float2 dv[4] = {make_float2(dA.x, dA.y), make_float2(dA.z, dA.w), make_float2(dB.x, dB.y),
-                                make_float2(dB.z, dB.w)};
-                float2 wv[4] = {make_float2(wA.x, wA.y), make_float2(wA.z, wA.w), make_float2(wB.x, wB.y),
-                                make_float2(wB.z, wB.w)};
-                if (!PREP) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float rx = sqrtf(wv[j].x), ry = sqrtf(wv[j].y);
-                        dv[j] = make_float2(dv[j].x * rx, dv[j].y * ry);
-                        wv[j] = make_float2(-rx, -ry);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const float2 r0 = __ffma2_rn(wv[j], m[j], dv[j]);
-                    const float2 r1 = __ffma2_rn(wv[2 + j], m[2 + j], dv[2 + j]);
-                    s0 = __ffma2_rn(r0, r0, s0);
-                    s1 = __ffma2_rn(r1, r1, s1);
-                }
-                rp += G::RG * 2 * K;
-                dp += G::RG * NX;
-                wp += G::RG * NX;
-            }
-            acc += (double)((s0.x + s0.y) + (s1.x + s1.y));
-            if (TEAM > 1) {
-                rp += SKIP * 2 * K;
-                dp += SKIP * NX;
-                wp += SKIP * NX;
-                if (STORE) mp += SKIP * NX;
-            }
-        }
+        // segments of this panel: [0,wlo) none, [wlo,nlo) wings, [nlo,nhi] all, (nhi,whi] wings, rest none
+        const bool n_on = ((cf.pan[0] >> pan) & 1u) && cf.lo[0] <= cf.hi[0];
+        const bool w_on = ((cf.pan[1] >> pan) & 1u) && cf.lo[1] <= cf.hi[1];
+        int nlo = n_on ? cf.lo[0] : STEPS, nhi1 = n_on ? cf.hi[0] + 1 : STEPS;   // [nlo, nhi1)
+        int wlo = w_on ? cf.lo[1] : nlo, whi1 = w_on ? cf.hi[1] + 1 : nhi1;      // [wlo, whi1)
+        wlo = min(wlo, nlo);               // the wing interval is widened to contain the core interval:
+        whi1 = max(whi1, nhi1);            // evaluating a component where it is not needed is harmless
+        if (!n_on) { nlo = whi1; nhi1 = whi1; }
+        // exponentials this evaluation really computes (whole team), for the roofline accounting
+        if (exps) *exps += (unsigned)(G::PW * G::RG) * (unsigned)((nhi1 - nlo) * NB + (whi1 - wlo) * NB);
+        acc += row_steps<NB, NX, NY, STORE, PREP, TEAM, 0>(cf, xd, 0, wlo, tw, g, colA, colB, rt, d, w, model_out);
+        acc += row_steps<NB, NX, NY, STORE, PREP, TEAM, 1>(cf, xd, wlo, nlo, tw, g, colA, colB, rt, d, w, model_out);
+        acc += row_steps<NB, NX, NY, STORE, PREP, TEAM, 2>(cf, xd, nlo, nhi1, tw, g, colA, colB, rt, d, w, model_out);
+        acc += row_steps<NB, NX, NY, STORE, PREP, TEAM, 1>(cf, xd, nhi1, whi1, tw, g, colA, colB, rt, d, w, model_out);
+        acc += row_steps<NB, NX, NY, STORE, PREP, TEAM, 0>(cf, xd, whi1, STEPS, tw, g, colA, colB, rt, d, w, model_out);
     }
     return warp_sum_f64(acc);
 }

@@ -126,17 +126,17 @@ class GibbsSampler:
 
     def stats(self, moments=True):
         """Batch statistics reduced on the device (K4).  Returns a dict of device tensors:
-        tries[P], accepts[P], min_tries (scalar), moments [F, P+1, 3], walkers_per_frame [F],
-        rows (scalar)."""
+        tries[P], accepts[P], min_tries (scalar), exps (scalar: exponentials really evaluated),
+        moments [F, P+1, 3], walkers_per_frame [F], rows (scalar)."""
         dev = self.domain.device
         pn, nf = self.nparam, self.domain.n_frames
-        tot = torch.empty((2 * pn + 1,), dtype=torch.int64, device=dev)
+        tot = torch.empty((2 * pn + 2,), dtype=torch.int64, device=dev)
         mom = torch.empty((nf, pn + 1, 3), dtype=torch.float64, device=dev) if moments else None
         cnt = torch.empty((nf + 1,), dtype=torch.int64, device=dev)
         _lib.check(self.lib.lapf_sampler_stats(self._h, tot.data_ptr(),
                                                mom.data_ptr() if mom is not None else None,
                                                cnt.data_ptr(), _stream_ptr(dev)))
-        return {"tries": tot[:pn], "accepts": tot[pn:2 * pn], "min_tries": tot[2 * pn],
+        return {"tries": tot[:pn], "accepts": tot[pn:2 * pn], "min_tries": tot[2 * pn], "exps": tot[2 * pn + 1],
                 "moments": mom, "walkers_per_frame": cnt[:nf], "rows": cnt[nf]}
 
 
