@@ -313,7 +313,8 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         const int which = (k == L::I_SX2 || k == L::I_SY2 || k == L::I_TH2) ? 1 : 0;
         if (shape_moved) load_shape<NB>(cf, which, ws.tf);
         build_row_table<NB, NY>(rt, cf, lane);
-        if (a.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
+        // in a team the update time is set by the warp with the busiest rows: culling cannot help there
+        if (TEAM == 1 && a.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
         unsigned e_upd = 0;
         double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw, &e_upd);   // :314-316
         n_exps += e_upd;

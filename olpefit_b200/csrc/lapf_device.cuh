@@ -417,11 +417,24 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
         if (!n_on) { nlo = whi1; nhi1 = whi1; }
         // exponentials this evaluation really computes (whole team), for the roofline accounting
         if (exps) *exps += (unsigned)(G::PW * G::RG) * (unsigned)((nhi1 - nlo) * NB + (whi1 - wlo) * NB);
-        acc += row_steps<NB, NX, NY, STORE, PREP, TEAM, 0>(cf, xd, 0, wlo, tw, g, colA, colB, rt, d, w, model_out);
-        acc += row_steps<NB, NX, NY, STORE, PREP, TEAM, 1>(cf, xd, wlo, nlo, tw, g, colA, colB, rt, d, w, model_out);
-        acc += row_steps<NB, NX, NY, STORE, PREP, TEAM, 2>(cf, xd, nlo, nhi1, tw, g, colA, colB, rt, d, w, model_out);
-        acc += row_steps<NB, NX, NY, STORE, PREP, TEAM, 1>(cf, xd, nhi1, whi1, tw, g, colA, colB, rt, d, w, model_out);
-        acc += row_steps<NB, NX, NY, STORE, PREP, TEAM, 0>(cf, xd, whi1, STEPS, tw, g, colA, colB, rt, d, w, model_out);
+        if (TEAM == 1) {
+            acc += row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, 0, wlo, 0, g, colA, colB, rt, d, w, model_out);
+            acc += row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, wlo, nlo, 0, g, colA, colB, rt, d, w, model_out);
+            acc += row_steps<NB, NX, NY, STORE, PREP, 1, 2>(cf, xd, nlo, nhi1, 0, g, colA, colB, rt, d, w, model_out);
+            acc += row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, nhi1, whi1, 0, g, colA, colB, rt, d, w, model_out);
+            acc += row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, whi1, STEPS, 0, g, colA, colB, rt, d, w, model_out);
+        } else {
+            // a team member owns only STEPS/TEAM steps: pick the kind per step
+#pragma unroll 1
+            for (int i = tw; i < STEPS; i += TEAM) {
+                if (i >= nlo && i < nhi1)
+                    acc += row_steps<NB, NX, NY, STORE, PREP, 1, 2>(cf, xd, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
+                else if (i >= wlo && i < whi1)
+                    acc += row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
+                else
+                    acc += row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
+            }
+        }
     }
     return warp_sum_f64(acc);
 }
