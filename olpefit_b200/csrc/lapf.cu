@@ -115,7 +115,7 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
     load_shape<NB>(cf, 1, tf[warp]);
     __shared__ __align__(16) float rt[4][NY * 4 * NB];
     build_row_table<NB, NY>(rt[warp], cf, lane);
-    if (pr.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
+    if (NX >= 64 && pr.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
     const size_t off = (size_t)f * NX * NY;
     double chi = warp_chi2<NB, NX, NY, STORE, false>(cf, rt[warp], pr.data + off, pr.weight + off,
                                                            STORE ? model_out + (size_t)b * NX * NY : nullptr, lane);
@@ -314,7 +314,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         if (shape_moved) load_shape<NB>(cf, which, ws.tf);
         build_row_table<NB, NY>(rt, cf, lane);
         // in a team the update time is set by the warp with the busiest rows: culling cannot help there
-        if (TEAM == 1 && a.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
+        if (NX >= 64 && TEAM == 1 && a.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
         unsigned e_upd = 0;
         double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw, &e_upd);   // :314-316
         n_exps += e_upd;

@@ -206,19 +206,42 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
     constexpr int K = 2 * NB;
     static_assert(NY % 32 == 0, "row table is built 32 rows at a time");
     __syncwarp();   // readers of the previous table are done
+    if (NY % 64 == 0) {
+        // two rows (r, r+32) per pass, as the two halves of packed FP32 operations
 #pragma unroll
-    for (int r0 = 0; r0 < NY; r0 += 32) {
-        const float fr = (float)(r0 + lane);
-        float v[2 * K];
+        for (int r0 = 0; r0 < NY; r0 += 64) {
+            const float2 fr = make_float2((float)(r0 + lane), (float)(r0 + 32 + lane));
+            float2 v[2 * K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float yd = fr - cf.y0[k];
-            v[k] = cf.sb[k & 1] * yd;
-            v[K + k] = (cf.sc[k & 1] * yd) * yd;
+            for (int k = 0; k < K; ++k) {
+                const float2 yd = __fadd2_rn(fr, make_float2(-cf.y0[k], -cf.y0[k]));
+                const float2 sc2 = make_float2(cf.sc[k & 1], cf.sc[k & 1]);
+                v[k] = __fmul2_rn(make_float2(cf.sb[k & 1], cf.sb[k & 1]), yd);
+                v[K + k] = __fmul2_rn(__fmul2_rn(sc2, yd), yd);
+            }
+            float4* o0 = reinterpret_cast<float4*>(rt + (r0 + lane) * 2 * K);
+            float4* o1 = reinterpret_cast<float4*>(rt + (r0 + 32 + lane) * 2 * K);
+#pragma unroll
+            for (int q = 0; q < 2 * K / 4; ++q) {
+                o0[q] = make_float4(v[4 * q].x, v[4 * q + 1].x, v[4 * q + 2].x, v[4 * q + 3].x);
+                o1[q] = make_float4(v[4 * q].y, v[4 * q + 1].y, v[4 * q + 2].y, v[4 * q + 3].y);
+            }
         }
-        float4* o = reinterpret_cast<float4*>(rt + (r0 + lane) * 2 * K);
+    } else {
 #pragma unroll
-        for (int q = 0; q < 2 * K / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int r0 = 0; r0 < NY; r0 += 32) {
+            const float fr = (float)(r0 + lane);
+            float v[2 * K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float yd = fr - cf.y0[k];
+                v[k] = cf.sb[k & 1] * yd;
+                v[K + k] = (cf.sc[k & 1] * yd) * yd;
+            }
+            float4* o = reinterpret_cast<float4*>(rt + (r0 + lane) * 2 * K);
+#pragma unroll
+            for (int q = 0; q < 2 * K / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
     }
     __syncwarp();
 }
@@ -226,8 +249,9 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
 // Far-field culling.  |A_k| 2^(q) <= |A_k| 2^(kappa dy^2) for every pixel of a row at distance dy
 // from the component's centre (kappa = sc - sb^2/(4 sa), the exponent maximised over dx), and the
 // same with the roles of x and y swapped for a column panel.  A component whose bound over a whole
-// row step (or panel) is below tau = 2^-24 |floor| cannot change the FP32 model value there -- the
-// model is at least of the size of the floor -- so those rows skip it: no MUFU, no FFMA.  Rows are
+// row step (or panel) is below tau = 2^-25 |floor| -- less than half an ulp of a model value that is
+// at least the floor -- would be rounded away by the FMA that adds it, so those rows skip it: no
+// MUFU, no FFMA, and (for non-negative amplitudes) bit-identical results.  Rows are
 // culled per CLASS (all narrow cores / all wide wings): the active rows of a class are one interval
 // of row steps, so a panel is walked as at most five segments (none, wings, all, wings, none), each
 // a tight loop without per-row tests.  On a 128-pixel stamp the cores matter in ~1/4 of the rows and
@@ -246,15 +270,16 @@ __device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
         if (lane == k) { a = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
     const int sh = lane & 1;
     const float sa = sh ? cf.sa[1] : cf.sa[0], sb = sh ? cf.sb[1] : cf.sb[0], sc = sh ? cf.sc[1] : cf.sc[0];
-    const float tau = 0x1p-24f * fabsf(cf.floor);
-    const float L = log2f(fabsf(a) / tau);                 // bits of headroom above tau
+    // approximate log2 / divide / sqrt are fine here: the radius gets a whole pixel of slack
+    const float tau = 0x1p-25f * fabsf(cf.floor);
+    const float L = __log2f(__fdividef(fabsf(a), tau));    // bits of headroom above tau
     int lo = 0, hi = STEPS - 1;                            // default: everything (also for nan / inf)
     uint32_t pm = kAllPans;
     if (L <= 0.f) {                                        // below tau everywhere
         lo = STEPS; hi = -1; pm = 0u;
     } else {
-        const float ky = sc - sb * sb / (4.f * sa), kx = sa - sb * sb / (4.f * sc);   // both < 0
-        const float Y = sqrtf(L / -ky) + 1.f, X = sqrtf(L / -kx) + 1.f;              // + one pixel of slack
+        const float ky = sc - __fdividef(sb * sb, 4.f * sa), kx = sa - __fdividef(sb * sb, 4.f * sc);   // both < 0
+        const float Y = __fsqrt_rn(__fdividef(L, -ky)) + 1.f, X = __fsqrt_rn(__fdividef(L, -kx)) + 1.f;
         if (Y < 1e6f && fabsf(y0) < 1e6f) {
             lo = max(0, (int)ceilf((y0 - Y - (float)(G::RG - 1)) / (float)G::RG));
             hi = min(STEPS - 1, (int)floorf((y0 + Y) / (float)G::RG));
@@ -290,8 +315,8 @@ __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
 }
 
 // Row steps [i0, i1) of one panel for the component classes KIND says (0: none, the model is the
-// floor; 1: wide wings only; 2: all components).  Returns the FP32-accumulated chi-square of these
-// rows as FP64.  PREP = true: the planes hold d*sqrt(w) and -sqrt(w) (the sampler converts a stamp
+// floor; 1: wide wings only; 2: all components).  chi-square terms are added to the four FP32
+// accumulators s0, s1 in row order, whatever the segmentation (so culling does not regroup sums).  PREP = true: the planes hold d*sqrt(w) and -sqrt(w) (the sampler converts a stamp
 // once after staging it); PREP = false: raw data / weight planes, converted per pixel.  Both give
 // bit-identical chi-square: the residual is always  r = fma(-sqrt(w), m, d*sqrt(w)),  chi2 += r*r.
 //
@@ -300,21 +325,20 @@ __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
 // 3 FFMA2 + 2 MUFU.EX2, which keeps the issue slots needed per MUFU below the SFU's own rate
 // (measured: a MUFU costs ~4 issue cycles), so the loop is SFU-bound.
 template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM, int KIND>
-__device__ __forceinline__ double row_steps(const Coef<NB>& cf, const float2 (&xd)[2 * NB][4], int i0, int i1,
-                                            int tw, int g, int colA, int colB, const float* __restrict__ rt,
-                                            const float* __restrict__ d, const float* __restrict__ w,
-                                            float* __restrict__ model_out) {
+__device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)[2 * NB][4], float2& s0, float2& s1,
+                                          int i0, int i1, int tw, int g, int colA, int colB,
+                                          const float* __restrict__ rt, const float* __restrict__ d,
+                                          const float* __restrict__ w, float* __restrict__ model_out) {
     using G = Geo<NX>;
     constexpr int K = 2 * NB;
     // first step >= i0 that belongs to warp tw of the team
     int i = i0 + ((tw - i0) % TEAM + TEAM) % TEAM;
-    if (i >= i1) return 0.0;
+    if (i >= i1) return;
     const int r0 = i * G::RG + g;
     const float* rp = rt + r0 * 2 * K;
     const float* dp = d + r0 * NX;
     const float* wp = w + r0 * NX;
     float* mp = STORE ? model_out + r0 * NX : nullptr;
-    float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (; i < i1; i += TEAM) {
         const float4 dA = *reinterpret_cast<const float4*>(dp + colA);
@@ -374,8 +398,6 @@ __device__ __forceinline__ double row_steps(const Coef<NB>& cf, const float2 (&x
         dp += TEAM * G::RG * NX;
         wp += TEAM * G::RG * NX;
     }
-    // FP32 partial sums of one segment (at most NY/RG steps x 8 pixels over 4 accumulators)
-    return (double)((s0.x + s0.y) + (s1.x + s1.y));
 }
 
 // chi-square of one parameter vector over the stamp by ONE warp (TEAM = 1), or this warp's share
@@ -399,12 +421,15 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
         const int colA = pan * G::PW + 4 * c + (G::PW / 2) * swap;
         const int colB = pan * G::PW + 4 * c + (G::PW / 2) * (1 - swap);
         float2 xd[K][4];   // pixel pairs: (0,1) (2,3) of group A, (0,1) (2,3) of group B
+        {
+            const float fa = (float)colA, fb = (float)colB;
+            const float2 cols[4] = {make_float2(fa, fa + 1.f), make_float2(fa + 2.f, fa + 3.f),
+                                    make_float2(fb, fb + 1.f), make_float2(fb + 2.f, fb + 3.f)};
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
+            for (int k = 0; k < K; ++k) {
+                const float2 nx0 = make_float2(-cf.x0[k], -cf.x0[k]);
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                xd[k][jj] = make_float2((float)(colA + 2 * jj) - cf.x0[k], (float)(colA + 2 * jj + 1) - cf.x0[k]);
-                xd[k][2 + jj] = make_float2((float)(colB + 2 * jj) - cf.x0[k], (float)(colB + 2 * jj + 1) - cf.x0[k]);
+                for (int j = 0; j < 4; ++j) xd[k][j] = __fadd2_rn(cols[j], nx0);
             }
         }
         // segments of this panel: [0,wlo) none, [wlo,nlo) wings, [nlo,nhi] all, (nhi,whi] wings, rest none
@@ -417,24 +442,30 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
         if (!n_on) { nlo = whi1; nhi1 = whi1; }
         // exponentials this evaluation really computes (whole team), for the roofline accounting
         if (exps) *exps += (unsigned)(G::PW * G::RG) * (unsigned)((nhi1 - nlo) * NB + (whi1 - wlo) * NB);
-        if (TEAM == 1) {
-            acc += row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, 0, wlo, 0, g, colA, colB, rt, d, w, model_out);
-            acc += row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, wlo, nlo, 0, g, colA, colB, rt, d, w, model_out);
-            acc += row_steps<NB, NX, NY, STORE, PREP, 1, 2>(cf, xd, nlo, nhi1, 0, g, colA, colB, rt, d, w, model_out);
-            acc += row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, nhi1, whi1, 0, g, colA, colB, rt, d, w, model_out);
-            acc += row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, whi1, STEPS, 0, g, colA, colB, rt, d, w, model_out);
+        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+        if (NX < 64) {
+            // 32-pixel stamps have no far field (set_cull is never called for them): one dense segment
+            row_steps<NB, NX, NY, STORE, PREP, TEAM, 2>(cf, xd, s0, s1, 0, STEPS, tw, g, colA, colB, rt, d, w, model_out);
+        } else if (TEAM == 1) {
+            row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, s0, s1, 0, wlo, 0, g, colA, colB, rt, d, w, model_out);
+            row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, s0, s1, wlo, nlo, 0, g, colA, colB, rt, d, w, model_out);
+            row_steps<NB, NX, NY, STORE, PREP, 1, 2>(cf, xd, s0, s1, nlo, nhi1, 0, g, colA, colB, rt, d, w, model_out);
+            row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, s0, s1, nhi1, whi1, 0, g, colA, colB, rt, d, w, model_out);
+            row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, s0, s1, whi1, STEPS, 0, g, colA, colB, rt, d, w, model_out);
         } else {
             // a team member owns only STEPS/TEAM steps: pick the kind per step
 #pragma unroll 1
             for (int i = tw; i < STEPS; i += TEAM) {
                 if (i >= nlo && i < nhi1)
-                    acc += row_steps<NB, NX, NY, STORE, PREP, 1, 2>(cf, xd, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
+                    row_steps<NB, NX, NY, STORE, PREP, 1, 2>(cf, xd, s0, s1, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
                 else if (i >= wlo && i < whi1)
-                    acc += row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
+                    row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, s0, s1, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
                 else
-                    acc += row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
+                    row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, s0, s1, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
             }
         }
+        // FP32 partial sums of one panel (at most NY/RG steps x 8 pixels over 4 accumulators) -> FP64
+        acc += (double)((s0.x + s0.y) + (s1.x + s1.y));
     }
     return warp_sum_f64(acc);
 }
