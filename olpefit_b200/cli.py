@@ -181,6 +181,16 @@ def run(kind, nbody, argv=None):
     if packed is not None:
         packed.close(count=sam.count)
 
+    # Gelman-Rubin statistic of the recorded rows (apf_step3.py:260-278) from device-side moments,
+    # summed over ranks: a convergence read-out without re-reading any chain file
+    if kind != "step2a" and total_walkers > 1:
+        stt = sam.stats(moments=True)
+        mom = dist.allreduce_sum(stt["moments"] if n_local else torch.zeros_like(stt["moments"]))
+        n_rows = int(stt["rows"].item())
+        if n_rows > 1:
+            _, rc = chains.gelman_rubin_from_moments(mom[0, :P].cpu().numpy(), n_rows, total_walkers)
+            say("Gelman-Rubin stat per parameter (recorded rows, all walkers):", np.round(rc, 4))
+            say("GR for positions:", *np.round(rc[:2 * nbody], 4))
     _, tr, ac = sam.state()
     tr, ac = tr.cpu().numpy(), ac.cpu().numpy()
     for i in range(n_local):

@@ -406,14 +406,16 @@ class ChainResult:
 
 def run_chain(data, weight, layout: Layout, p0, stream, *, origin=(0, 0), n_updates=None,
               accept_min=None, burn_in=0, thin=1, floor_index=None, widths=None,
-              record_trace=False, chi0=None):
+              record_trace=False, chi0=None, chi2_fn=None):
     """One walker of the reference loop (apf_step2.py:276-351; step 2a: apf_step2a.py:271-337).
 
     ``data``/``weight`` are the pixel domain (full frame or a cut-out whose lower-left pixel
     is ``origin`` in frame coordinates; parameters stay in frame coordinates).  Stops after
     ``n_updates`` (step 2a rule) or when min(tries) >= accept_min (step 2 rule, :300).
     A chain row is appended after every ``thin``-th update once count >= burn_in (:342-351),
-    whether or not the proposal was accepted.
+    whether or not the proposal was accepted.  ``chi2_fn(p) -> float`` replaces the
+    build_analytical_model + chi_squared pair (:314-316), which is how the tests drive the device
+    operator from the reference's host loop.
     """
     ny, nx = data.shape
     grid = pixel_grid(ny, nx, origin)
@@ -423,9 +425,11 @@ def run_chain(data, weight, layout: Layout, p0, stream, *, origin=(0, 0), n_upda
     w = np.asarray(layout.widths if widths is None else widths, dtype=np.float64)
     tries = np.zeros(npar)
     accepts = np.zeros(npar)
-    chi = chi_squared_weighted(data, model_image(p, layout, ny, nx, grid=grid,
-                                                 floor_index=floor_index), weight) \
-        if chi0 is None else chi0
+    if chi2_fn is None:
+        def chi2_fn(q):
+            return chi_squared_weighted(data, model_image(q, layout, ny, nx, grid=grid,
+                                                          floor_index=floor_index), weight)
+    chi = chi2_fn(p) if chi0 is None else chi0
     rows = [np.full(npar + 1, np.nan)]                       # :278-279
     trace = []
     count = 0
@@ -440,8 +444,7 @@ def run_chain(data, weight, layout: Layout, p0, stream, *, origin=(0, 0), n_upda
         trial = p.copy()                                     # :312-313
         trial[k] = new
         with np.errstate(all="ignore"):
-            chi_t = chi_squared_weighted(data, model_image(trial, layout, ny, nx, grid=grid,
-                                                           floor_index=floor_index), weight)
+            chi_t = chi2_fn(trial)                           # :314-316
         ok = accept_rule(stream, count, chi, chi_t)          # :318
         if ok:                                               # :321-327
             accepts[k] += 1

@@ -449,3 +449,28 @@ def test_far_field_culling_changes_nothing_visible(gpu, nbody, size):
     bad[1, 2 * nbody + 3] = np.nan
     _, c_bad = on.model_chi2(bad)
     assert bool(np.all(np.isnan(c_bad.cpu().numpy())))
+
+
+def test_reference_host_loop_with_device_operator(gpu):
+    """INTEGRATION.md level 2: the reference's own host loop (here: the oracle's restatement of
+    apf_step2.py:300-351 on numpy's Mersenne-Twister stream) with build_analytical_model +
+    chi_squared swapped for the device operator follows the all-CPU chain."""
+    synth, model = gpu["synth"], gpu["model"]
+    lay = orc.layout_for(2)
+    ox, oy = synth.stamp_origin(64)
+    img, truth = synth.make_frame(0, 2, region=(oy, oy + 64, ox, ox + 64))
+    dom = _domain(gpu, img, (ox, oy), 2)
+    img64 = img.astype(np.float64)
+    w = orc.weight_map(img64, HEADER)
+    guess = synth.step1_guess(img, 2, origin=(ox, oy))
+    p0 = gpu["frame"].initial_parameters(img, guess, 2, origin=(ox, oy))
+    m = model.build_analytical_model(p0, dom).cpu().numpy()
+    ref = orc.model_image(p0, lay, 64, 64, origin=(ox, oy))
+    assert np.max(np.abs(m - ref) / np.abs(ref)) < RTOL
+    assert model.chi_squared(p0, dom) == pytest.approx(orc.chi_squared_weighted(img64, ref, w), rel=RTOL)
+    cpu = orc.run_chain(img64, w, lay, p0, orc.NumpyStream(77), origin=(ox, oy), n_updates=150)
+    dev = orc.run_chain(img64, w, lay, p0, orc.NumpyStream(77), origin=(ox, oy), n_updates=150,
+                        chi2_fn=lambda q: model.chi_squared(q, dom))
+    assert np.array_equal(dev.tries, cpu.tries) and np.array_equal(dev.accepts, cpu.accepts)
+    np.testing.assert_array_equal(dev.rows[1:, :-1], cpu.rows[1:, :-1])      # same decisions, same values
+    np.testing.assert_allclose(dev.rows[1:, -1], cpu.rows[1:, -1], rtol=RTOL)
