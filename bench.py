@@ -311,6 +311,9 @@ def run_b200(a):
                        "+ counters D2H to pinned host; wall clock per step, median over steps, max over ranks" % U}
 
     smp.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
 
