@@ -270,20 +270,28 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
 
     Coef<NB> cf;
     stage_trial<NB>(ws.tf, lane, p, oxd, oyd);
-    load_shape<NB>(cf, 0, ws.tf);
-    load_shape<NB>(cf, 1, ws.tf);
-    if (lane == 0) {
-        ws.shape[0] = cf.sa[0]; ws.shape[1] = cf.sb[0]; ws.shape[2] = cf.sc[0];
-        ws.shape[4] = cf.sa[1]; ws.shape[5] = cf.sb[1]; ws.shape[6] = cf.sc[1];
+    {
+        float s0, c0, s1, c1;
+        sincosf(ws.tf[L::I_TH], &s0, &c0);
+        sincosf(ws.tf[L::I_TH2], &s1, &c1);
+        set_shape_sc<NB>(cf, 0, ws.tf[L::I_SX], ws.tf[L::I_SY], s0, c0);
+        set_shape_sc<NB>(cf, 1, ws.tf[L::I_SX2], ws.tf[L::I_SY2], s1, c1);
+        if (lane == 0) {
+            ws.shape[0] = cf.sa[0]; ws.shape[1] = cf.sb[0]; ws.shape[2] = cf.sc[0];
+            ws.shape[4] = cf.sa[1]; ws.shape[5] = cf.sb[1]; ws.shape[6] = cf.sc[1];
+            ws.trig[0] = s0; ws.trig[1] = c0; ws.trig[2] = s1; ws.trig[3] = c1;
+        }
     }
 
-    int64_t next_rec = a.next_record;
-    int64_t row = 0;
+    // launch-relative 32-bit counters (lapf_sampler_run caps a launch at 2^30 updates)
+    const int n_upd = (int)a.n_updates;
+    int next_rec = (int)min(a.next_record - a.t0 - 1, (int64_t)0x7fffffff);   // update index that records next
+    int row = 0;
     unsigned long long n_exps = 0;
 
 #pragma unroll 1
-    for (int64_t u = 0; u < a.n_updates; ++u) {
-        const int slot = (int)(u & 31);
+    for (int u = 0; u < n_upd; ++u) {
+        const int slot = u & 31;
         if (slot == 0) {
             // lane l prepares the draws of update t0+u+l: 32 updates of random numbers at once
             const Draw dr = make_draw(a.seed, gid, (uint64_t)(a.t0 + u + lane), P);
@@ -309,9 +317,22 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
             cf.sa[0] = s0.x; cf.sb[0] = s0.y; cf.sc[0] = s0.z;
             cf.sa[1] = s1.x; cf.sb[1] = s1.y; cf.sc[1] = s1.z;
         }
+        // a shape parameter moved: redo that shape's a, b, c; sin/cos only if its angle moved
         const bool shape_moved = k >= L::I_SX;
         const int which = (k == L::I_SX2 || k == L::I_SY2 || k == L::I_TH2) ? 1 : 0;
-        if (shape_moved) load_shape<NB>(cf, which, ws.tf);
+        float tsin = 0.f, tcos = 1.f;
+        if (shape_moved) {
+            const float4 tg = *reinterpret_cast<const float4*>(&ws.trig[0]);
+            if (which) {
+                tsin = tg.z; tcos = tg.w;
+                if (k == L::I_TH2) sincosf(ws.tf[L::I_TH2], &tsin, &tcos);
+                set_shape_sc<NB>(cf, 1, ws.tf[L::I_SX2], ws.tf[L::I_SY2], tsin, tcos);
+            } else {
+                tsin = tg.x; tcos = tg.y;
+                if (k == L::I_TH) sincosf(ws.tf[L::I_TH], &tsin, &tcos);
+                set_shape_sc<NB>(cf, 0, ws.tf[L::I_SX], ws.tf[L::I_SY], tsin, tcos);
+            }
+        }
         build_row_table<NB, NY>(rt, cf, lane);
         // in a team the update time is set by the warp with the busiest rows: culling cannot help there
         if (NX >= 64 && TEAM == 1 && a.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
@@ -338,11 +359,13 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
             if (lane == k) p = nv;                                    // :325
             chi_c = chi_t;                                            // :327
             if (shape_moved && lane == 0) {   // constant indices only: keeps cf in registers
-                if (which) { ws.shape[4] = cf.sa[1]; ws.shape[5] = cf.sb[1]; ws.shape[6] = cf.sc[1]; }
-                else       { ws.shape[0] = cf.sa[0]; ws.shape[1] = cf.sb[0]; ws.shape[2] = cf.sc[0]; }
+                if (which) { ws.shape[4] = cf.sa[1]; ws.shape[5] = cf.sb[1]; ws.shape[6] = cf.sc[1];
+                             ws.trig[2] = tsin; ws.trig[3] = tcos; }
+                else       { ws.shape[0] = cf.sa[0]; ws.shape[1] = cf.sb[0]; ws.shape[2] = cf.sc[0];
+                             ws.trig[0] = tsin; ws.trig[1] = tcos; }
             }
         }
-        if (a.t0 + u + 1 == next_rec) {                               // :342-351
+        if (u == next_rec) {                                          // :342-351
             if (lane <= P && tw == 0) {
                 const size_t mi = (size_t)wl * (P + 1) + lane;
                 const double v = (lane == P) ? chi_c : p;
@@ -352,7 +375,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
                 atomicAdd(&a.moments[2 * mi + 1], dl * dl);
             }
             ++row;
-            next_rec += a.thin;
+            next_rec += a.thin;   // (saturates harmlessly: a launch is shorter than 2^30)
         }
     }
 
@@ -792,7 +815,7 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     if (cfg->n_walkers <= 0 || cfg->n_walkers > (int64_t)1 << 30)
         return fail(LAPF_ERR_INVALID, "n_walkers %lld out of range", (long long)cfg->n_walkers);
     if (!cfg->init_params) return fail(LAPF_ERR_INVALID, "init_params is NULL");
-    if (cfg->thin < 1) return fail(LAPF_ERR_INVALID, "thin must be >= 1");
+    if (cfg->thin < 1 || cfg->thin > (1 << 30)) return fail(LAPF_ERR_INVALID, "thin must be in [1, 2^30]");
     if (cfg->burn_in < 0) return fail(LAPF_ERR_INVALID, "burn_in must be >= 0");
     if (cfg->team_warps != 0 && cfg->team_warps != 1 && cfg->team_warps != 4 && cfg->team_warps != 16)
         return fail(LAPF_ERR_INVALID, "team_warps %d not supported (0, 1, 4 or 16)", cfg->team_warps);
@@ -917,7 +940,8 @@ int64_t lapf_sampler_launches(const lapf_sampler* s) { return s ? s->launches : 
 
 int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int64_t rows_cap, void* stream) {
     if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
-    if (n_updates < 0) return fail(LAPF_ERR_INVALID, "n_updates < 0");
+    if (n_updates < 0 || n_updates > ((int64_t)1 << 30))
+        return fail(LAPF_ERR_INVALID, "n_updates must be in [0, 2^30] per launch");
     if (n_updates == 0) return LAPF_OK;
     const int64_t rows = lapf_sampler_rows_for(s, n_updates);
     if (chain_out && rows_cap < rows)

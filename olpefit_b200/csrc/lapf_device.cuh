@@ -116,13 +116,18 @@ struct Coef {
 // a, b, c of astropy Gaussian2D.evaluate, pre-scaled so that the
 // exponential is a bare ex2:  G = A * 2^(sa*dx^2 + sb*dx*dy + sc*dy^2).
 template <int NB>
-__device__ __forceinline__ void set_shape(Coef<NB>& cf, int which, float sx, float sy, float th) {
-    float s, c;
-    sincosf(th, &s, &c);
+__device__ __forceinline__ void set_shape_sc(Coef<NB>& cf, int which, float sx, float sy, float s, float c) {
     const float ivx = 1.0f / (sx * sx), ivy = 1.0f / (sy * sy);
     cf.sa[which] = -0.5f * kLog2e * (c * c * ivx + s * s * ivy);
     cf.sb[which] = -kLog2e * (s * c) * (ivx - ivy);     // sin(2t)/2 = s*c
     cf.sc[which] = -0.5f * kLog2e * (s * s * ivx + c * c * ivy);
+}
+
+template <int NB>
+__device__ __forceinline__ void set_shape(Coef<NB>& cf, int which, float sx, float sy, float th) {
+    float s, c;
+    sincosf(th, &s, &c);
+    set_shape_sc<NB>(cf, which, sx, sy, s, c);
 }
 
 // Per-warp staging of one (trial) parameter vector as FP32 in shared memory.  Lane j < P holds
@@ -285,7 +290,7 @@ __device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
             hi = min(STEPS - 1, (int)floorf((y0 + Y) / (float)G::RG));
             if (lo > hi) { lo = STEPS; hi = -1; }
         }
-        if (X < 1e6f && fabsf(x0) < 1e6f) {
+        if (G::PANELS > 1 && X < 1e6f && fabsf(x0) < 1e6f) {
             pm = 0u;
 #pragma unroll
             for (int p = 0; p < G::PANELS; ++p)
@@ -324,23 +329,24 @@ __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
 // instruction, scalar coefficients as broadcast operands.  Per pixel PAIR and component that is
 // 3 FFMA2 + 2 MUFU.EX2, which keeps the issue slots needed per MUFU below the SFU's own rate
 // (measured: a MUFU costs ~4 issue cycles), so the loop is SFU-bound.
-template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM, int KIND>
+struct StepPtrs {          // where the next row step of this lane lives
+    const float* rp;       // row table
+    const float* dp;       // data plane
+    const float* wp;       // weight plane
+    float* mp;             // model output (STORE only)
+};
+
+template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND>
 __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)[2 * NB][4], float2& s0, float2& s1,
-                                          int i0, int i1, int tw, int g, int colA, int colB,
-                                          const float* __restrict__ rt, const float* __restrict__ d,
-                                          const float* __restrict__ w, float* __restrict__ model_out) {
+                                          int& i, int i1, StepPtrs& sp, int colA, int colB) {
     using G = Geo<NX>;
     constexpr int K = 2 * NB;
-    // first step >= i0 that belongs to warp tw of the team
-    int i = i0 + ((tw - i0) % TEAM + TEAM) % TEAM;
-    if (i >= i1) return;
-    const int r0 = i * G::RG + g;
-    const float* rp = rt + r0 * 2 * K;
-    const float* dp = d + r0 * NX;
-    const float* wp = w + r0 * NX;
-    float* mp = STORE ? model_out + r0 * NX : nullptr;
+    const float* rp = sp.rp;
+    const float* dp = sp.dp;
+    const float* wp = sp.wp;
+    float* mp = sp.mp;
 #pragma unroll 1
-    for (; i < i1; i += TEAM) {
+    for (; i < i1; ++i) {
         const float4 dA = *reinterpret_cast<const float4*>(dp + colA);
         const float4 dB = *reinterpret_cast<const float4*>(dp + colB);
         const float4 wA = *reinterpret_cast<const float4*>(wp + colA);
@@ -373,7 +379,7 @@ __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)
         if (STORE) {
             *reinterpret_cast<float4*>(mp + colA) = make_float4(m[0].x, m[0].y, m[1].x, m[1].y);
             *reinterpret_cast<float4*>(mp + colB) = make_float4(m[2].x, m[2].y, m[3].x, m[3].y);
-            mp += TEAM * G::RG * NX;
+            mp += G::RG * NX;
         }
         float2 dv[4] = {make_float2(dA.x, dA.y), make_float2(dA.z, dA.w), make_float2(dB.x, dB.y),
                         make_float2(dB.z, dB.w)};
@@ -394,10 +400,11 @@ __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)
             s0 = __ffma2_rn(ra, ra, s0);
             s1 = __ffma2_rn(rb, rb, s1);
         }
-        rp += TEAM * G::RG * 2 * K;
-        dp += TEAM * G::RG * NX;
-        wp += TEAM * G::RG * NX;
+        rp += G::RG * 2 * K;
+        dp += G::RG * NX;
+        wp += G::RG * NX;
     }
+    sp.rp = rp; sp.dp = dp; sp.wp = wp; sp.mp = mp;
 }
 
 // chi-square of one parameter vector over the stamp by ONE warp (TEAM = 1), or this warp's share
@@ -443,25 +450,28 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __r
         // exponentials this evaluation really computes (whole team), for the roofline accounting
         if (exps) *exps += (unsigned)(G::PW * G::RG) * (unsigned)((nhi1 - nlo) * NB + (whi1 - wlo) * NB);
         float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
-        if (NX < 64) {
-            // 32-pixel stamps have no far field (set_cull is never called for them): one dense segment
-            row_steps<NB, NX, NY, STORE, PREP, TEAM, 2>(cf, xd, s0, s1, 0, STEPS, tw, g, colA, colB, rt, d, w, model_out);
-        } else if (TEAM == 1) {
-            row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, s0, s1, 0, wlo, 0, g, colA, colB, rt, d, w, model_out);
-            row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, s0, s1, wlo, nlo, 0, g, colA, colB, rt, d, w, model_out);
-            row_steps<NB, NX, NY, STORE, PREP, 1, 2>(cf, xd, s0, s1, nlo, nhi1, 0, g, colA, colB, rt, d, w, model_out);
-            row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, s0, s1, nhi1, whi1, 0, g, colA, colB, rt, d, w, model_out);
-            row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, s0, s1, whi1, STEPS, 0, g, colA, colB, rt, d, w, model_out);
+        if (TEAM == 1) {
+            // contiguous steps: the pointers run through the segments
+            StepPtrs sp{rt + g * 2 * K, d + g * NX, w + g * NX, STORE ? model_out + g * NX : nullptr};
+            int i = 0;
+            if (NX < 64) {
+                // 32-pixel stamps have no far field (set_cull is never called for them)
+                row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, STEPS, sp, colA, colB);
+            } else {
+                row_steps<NB, NX, NY, STORE, PREP, 0>(cf, xd, s0, s1, i, wlo, sp, colA, colB);
+                row_steps<NB, NX, NY, STORE, PREP, 1>(cf, xd, s0, s1, i, nlo, sp, colA, colB);
+                row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, nhi1, sp, colA, colB);
+                row_steps<NB, NX, NY, STORE, PREP, 1>(cf, xd, s0, s1, i, whi1, sp, colA, colB);
+                row_steps<NB, NX, NY, STORE, PREP, 0>(cf, xd, s0, s1, i, STEPS, sp, colA, colB);
+            }
         } else {
-            // a team member owns only STEPS/TEAM steps: pick the kind per step
+            // a team member owns only STEPS/TEAM steps (no culling in teams): one dense step at a time
 #pragma unroll 1
-            for (int i = tw; i < STEPS; i += TEAM) {
-                if (i >= nlo && i < nhi1)
-                    row_steps<NB, NX, NY, STORE, PREP, 1, 2>(cf, xd, s0, s1, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
-                else if (i >= wlo && i < whi1)
-                    row_steps<NB, NX, NY, STORE, PREP, 1, 1>(cf, xd, s0, s1, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
-                else
-                    row_steps<NB, NX, NY, STORE, PREP, 1, 0>(cf, xd, s0, s1, i, i + 1, 0, g, colA, colB, rt, d, w, model_out);
+            for (int it = tw; it < STEPS; it += TEAM) {
+                const int r0 = it * G::RG + g;
+                StepPtrs sp{rt + r0 * 2 * K, d + r0 * NX, w + r0 * NX, STORE ? model_out + r0 * NX : nullptr};
+                int i = it;
+                row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, it + 1, sp, colA, colB);
             }
         }
         // FP32 partial sums of one panel (at most NY/RG steps x 8 pixels over 4 accumulators) -> FP64
@@ -515,6 +525,7 @@ struct WarpScratch {
     double lnu[32];      // log of the accept/reject uniform of update slot i
     int k[32];           // parameter index of update slot i
     float shape[8];      // sa0 sb0 sc0 - sa1 sb1 sc1 -  of the CURRENT state
+    float trig[4];       // sin, cos of theta (narrow), sin, cos of theta2 (wide) of the CURRENT state
 };
 
 __device__ __forceinline__ Draw make_draw(uint64_t seed, uint64_t walker_id, uint64_t t, int nparam) {
