@@ -119,6 +119,20 @@ int lapf_sampler_destroy(lapf_sampler* s);
  * stream of epochs reuse one handle without reallocating device memory. */
 int lapf_sampler_reset(lapf_sampler* s, const double* init_params, uint64_t seed, void* stream);
 
+/* Checkpoint / resume.  A walker is (parameters, chi-square, counters, moments, update count) and
+ * its random stream is a pure function of (seed, walker id, update count), so a saved blob restores
+ * the batch exactly: run(a); save; ...; load; run(b) gives the bits of run(a+b).  The blob is a
+ * device buffer of lapf_sampler_checkpoint_bytes() bytes owned by the caller; load() expects a
+ * sampler created with the same shape (walkers, model, frame_of).  The reference's only resume
+ * point is the chain file / step2a.csv (apf_step2.py:248-256). */
+int64_t lapf_sampler_checkpoint_bytes(const lapf_sampler* s);
+int lapf_sampler_save(lapf_sampler* s, void* blob, int64_t blob_bytes, void* stream);
+int lapf_sampler_load(lapf_sampler* s, const void* blob, int64_t blob_bytes, void* stream);
+
+/* Replace the jump widths (HOST [P]) for the following runs.  The reference's widths are fixed
+ * (apf_step2.py:234); this exists for burn-in-only tuning, which the CLI offers as --adapt. */
+int lapf_sampler_set_widths(lapf_sampler* s, const double* widths);
+
 /* Chain rows a run of n_updates starting at the sampler's current count will produce. */
 int64_t lapf_sampler_rows_for(const lapf_sampler* s, int64_t n_updates);
 

@@ -39,6 +39,10 @@ SYMBOLS = {
     "lapf_sampler_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p), C.c_void_p]),
     "lapf_sampler_destroy": (C.c_int, [C.c_void_p]),
     "lapf_sampler_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "lapf_sampler_checkpoint_bytes": (C.c_int64, [C.c_void_p]),
+    "lapf_sampler_save": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "lapf_sampler_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "lapf_sampler_set_widths": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "lapf_sampler_rows_for": (C.c_int64, [C.c_void_p, C.c_int64]),
     "lapf_sampler_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "lapf_sampler_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

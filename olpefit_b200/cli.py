@@ -48,6 +48,13 @@ def _parser(kind):
     ap.add_argument("--format", choices=["csv", "bin"], default="csv", help="per-walker reference CSV files, or one packed binary")
     ap.add_argument("--fix-bkgd", action="store_true",
                     help="2-body only: use bkgd (p[9]) as the constant floor instead of the reference's p[12]")
+    ap.add_argument("--adapt", action="store_true",
+                    help="tune the jump widths from the acceptance rates DURING BURN-IN ONLY (the reference's widths "
+                         "are fixed; off by default so posteriors compare like for like)")
+    ap.add_argument("--checkpoint", action="store_true",
+                    help="write <results>/checkpoint_rank<r>.pt when done (exact state of every walker)")
+    ap.add_argument("--resume", action="store_true",
+                    help="continue from <results>/checkpoint_rank<r>.pt, appending to the existing chain files")
     ap.add_argument("--quiet", action="store_true")
     return ap
 
@@ -144,6 +151,16 @@ def run(kind, nbody, argv=None):
 
     streamer = smp.ChainStreamer(sam, args.segment)
     first = [True]
+    ckpt_path = outdir + "checkpoint_rank%d.pt" % rank
+    if args.resume:
+        ck = torch.load(ckpt_path)
+        if ck["n_walkers"] != sam.n_walkers or ck["nbody"] != nbody:
+            raise SystemExit("checkpoint %s does not match this run" % ckpt_path)
+        sam.load(ck["blob"])
+        seed = ck["seed"]
+        first[0] = False                      # append to the chain files that are already there
+        say("Resumed at update", sam.count)
+    widths, _is_log = layout.default_widths(nbody)
 
     def consume(seg):
         if seg is None or n_local == 0:
@@ -170,6 +187,13 @@ def run(kind, nbody, argv=None):
                 break
             # min(tries) grows by at most one per update: `gap` updates can never overshoot
             n = min(args.segment, gap)
+            if args.adapt and sam.count < burn_in:
+                # burn-in only: nudge each width towards ~35% acceptance, then leave it alone
+                n = min(n, max(burn_in - sam.count, 1), 512)
+                if sam.count > 0:
+                    rate = (accepts.double() / tries.double().clamp(min=1)).cpu().numpy()
+                    widths = widths * np.clip(np.exp(rate - 0.35), 0.5, 2.0)
+                    sam.set_widths(widths)
             consume(streamer.run(n))
             if sam.count % (10 * args.segment) < n:
                 say("Loop count:", sam.count, " min tries:", int(mn.item()),
@@ -180,6 +204,11 @@ def run(kind, nbody, argv=None):
             chains.write_walker_csv(pth, np.zeros((0, P + 1)))
     if packed is not None:
         packed.close(count=sam.count)
+    if args.adapt:
+        say("Jump widths after burn-in tuning:", widths)
+    if args.checkpoint and n_local:
+        torch.save({"blob": sam.save().cpu(), "n_walkers": sam.n_walkers, "nbody": nbody, "seed": seed,
+                    "count": sam.count}, ckpt_path)
 
     # Gelman-Rubin statistic of the recorded rows (apf_step3.py:260-278) from device-side moments,
     # summed over ranks: a convergence read-out without re-reading any chain file

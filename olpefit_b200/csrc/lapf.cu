@@ -924,6 +924,62 @@ int lapf_sampler_reset(lapf_sampler* s, const double* init_params, uint64_t seed
     return LAPF_OK;
 }
 
+// Checkpoint layout (device blob, 8-byte units): [count][seed] state shift moments(2x) exps tries accepts
+static size_t checkpoint_bytes(const lapf_sampler* s) {
+    const size_t W = (size_t)s->cfg.n_walkers, P = (size_t)s->P, nst = W * (P + 1);
+    return 16 + sizeof(double) * nst * 4 + sizeof(unsigned long long) * W + sizeof(uint32_t) * W * P * 2;
+}
+
+int64_t lapf_sampler_checkpoint_bytes(const lapf_sampler* s) {
+    if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
+    return (int64_t)checkpoint_bytes(s);
+}
+
+static int checkpoint_copy(lapf_sampler* s, unsigned char* blob, bool save, cudaStream_t st) {
+    const size_t W = (size_t)s->cfg.n_walkers, P = (size_t)s->P, nst = W * (P + 1);
+    struct Part { void* dev; size_t bytes; } parts[] = {
+        {s->state, sizeof(double) * nst}, {s->shift, sizeof(double) * nst}, {s->moments, sizeof(double) * nst * 2},
+        {s->exps, sizeof(unsigned long long) * W}, {s->tries, sizeof(uint32_t) * W * P}, {s->accepts, sizeof(uint32_t) * W * P}};
+    size_t off = 16;
+    for (const Part& p : parts) {
+        CU(cudaMemcpyAsync(save ? (void*)(blob + off) : p.dev, save ? p.dev : (const void*)(blob + off), p.bytes,
+                           cudaMemcpyDeviceToDevice, st));
+        off += p.bytes;
+    }
+    return LAPF_OK;
+}
+
+int lapf_sampler_save(lapf_sampler* s, void* blob, int64_t blob_bytes, void* stream) {
+    if (!s || !blob) return fail(LAPF_ERR_INVALID, "sampler/blob is NULL");
+    if ((size_t)blob_bytes < checkpoint_bytes(s)) return fail(LAPF_ERR_INVALID, "checkpoint buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t head[2] = {s->count, (int64_t)s->cfg.seed};
+    CU(cudaMemcpyAsync(blob, head, 16, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // `head` lives on this stack frame
+    return checkpoint_copy(s, (unsigned char*)blob, true, st);
+}
+
+int lapf_sampler_load(lapf_sampler* s, const void* blob, int64_t blob_bytes, void* stream) {
+    if (!s || !blob) return fail(LAPF_ERR_INVALID, "sampler/blob is NULL");
+    if ((size_t)blob_bytes < checkpoint_bytes(s)) return fail(LAPF_ERR_INVALID, "checkpoint buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t head[2] = {0, 0};
+    CU(cudaMemcpyAsync(head, blob, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (head[0] < 0) return fail(LAPF_ERR_INVALID, "corrupt checkpoint (count %lld)", (long long)head[0]);
+    s->count = head[0];
+    s->cfg.seed = (uint64_t)head[1];
+    return checkpoint_copy(s, (unsigned char*)const_cast<void*>(blob), false, st);
+}
+
+int lapf_sampler_set_widths(lapf_sampler* s, const double* widths) {
+    if (!s || !widths) return fail(LAPF_ERR_INVALID, "sampler/widths is NULL");
+    for (int i = 0; i < s->P; ++i)
+        if (!(widths[i] >= 0.0)) return fail(LAPF_ERR_INVALID, "widths[%d] = %g is not a valid jump width", i, widths[i]);
+    for (int i = 0; i < s->P; ++i) s->widths[i] = widths[i];
+    return LAPF_OK;
+}
+
 int lapf_sampler_destroy(lapf_sampler* s) {
     free_sampler(s);
     return LAPF_OK;

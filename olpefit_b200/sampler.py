@@ -80,6 +80,26 @@ class GibbsSampler:
         _lib.check(self.lib.lapf_sampler_reset(self._h, p.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF,
                                                _stream_ptr(dev)))
 
+    def save(self):
+        """Checkpoint of the whole batch as a device uint8 tensor (see lapf_sampler_save)."""
+        n = int(_lib.check(self.lib.lapf_sampler_checkpoint_bytes(self._h)))
+        blob = torch.empty(n, dtype=torch.uint8, device=self.domain.device)
+        _lib.check(self.lib.lapf_sampler_save(self._h, blob.data_ptr(), n, _stream_ptr(self.domain.device)))
+        return blob
+
+    def load(self, blob):
+        """Restore a checkpoint made by ``save`` on a sampler of the same shape: the following runs
+        continue the chains bit for bit."""
+        blob = blob.to(self.domain.device).contiguous()
+        _lib.check(self.lib.lapf_sampler_load(self._h, blob.data_ptr(), blob.numel(), _stream_ptr(self.domain.device)))
+
+    def set_widths(self, widths):
+        """New jump widths for the following runs (burn-in tuning; the reference's are fixed)."""
+        w_np = np.ascontiguousarray(widths, dtype=np.float64)
+        if w_np.shape != (self.nparam,):
+            raise ValueError("widths must have %d entries" % self.nparam)
+        _lib.check(self.lib.lapf_sampler_set_widths(self._h, (C.c_double * self.nparam)(*w_np.tolist())))
+
     # -- the loop ------------------------------------------------------------------------
     @property
     def count(self) -> int:

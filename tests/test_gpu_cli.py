@@ -76,3 +76,24 @@ def test_step2_default_guess_packed_format_and_3body(tmp_path):
                            "--fix-bkgd", "--quiet"]) == 0
     c = np.genfromtxt(os.path.join(out2, "0_finalarray_mpi.csv"), delimiter=",")
     assert c.shape[1] == 17 and c.shape[0] > 10
+
+
+def test_checkpoint_resume_and_adapt_flags(tmp_path):
+    """--checkpoint / --resume continue the same chains (the files of an interrupted run followed
+    by its resumption equal the files of the uninterrupted run); --adapt only acts during burn-in."""
+    from olpefit_b200 import cli
+    common = ["--walkers", "4", "--burn-in", "0", "--seed", "21", "--stamp", "32", "--segment", "64", "--quiet"]
+    path_a, out_a, _ = _write_case(tmp_path, 2, tag="_whole")
+    assert cli.main_step2([path_a, "--accept-min", "24"] + common) == 0
+    whole = np.genfromtxt(os.path.join(out_a, "2_finalarray_mpi.csv"), delimiter=",")
+    path_b, out_b, _ = _write_case(tmp_path, 2, tag="_parts")
+    assert cli.main_step2([path_b, "--accept-min", "9", "--checkpoint"] + common) == 0
+    part = np.genfromtxt(os.path.join(out_b, "2_finalarray_mpi.csv"), delimiter=",")
+    assert os.path.exists(os.path.join(out_b, "checkpoint_rank0.pt")) and part.shape[0] < whole.shape[0]
+    assert cli.main_step2([path_b, "--accept-min", "24", "--resume"] + common) == 0
+    both = np.genfromtxt(os.path.join(out_b, "2_finalarray_mpi.csv"), delimiter=",")
+    assert both.shape == whole.shape and np.array_equal(both[1:], whole[1:])
+    path_c, out_c, _ = _write_case(tmp_path, 2, tag="_adapt")
+    assert cli.main_step2([path_c, "--accept-min", "40", "--adapt", "--walkers", "8", "--burn-in", "600",
+                           "--seed", "21", "--stamp", "32", "--quiet"]) == 0
+    assert np.genfromtxt(os.path.join(out_c, "0_finalarray_mpi.csv"), delimiter=",").shape[1] == 17

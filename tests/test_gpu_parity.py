@@ -474,3 +474,43 @@ def test_reference_host_loop_with_device_operator(gpu):
     assert np.array_equal(dev.tries, cpu.tries) and np.array_equal(dev.accepts, cpu.accepts)
     np.testing.assert_array_equal(dev.rows[1:, :-1], cpu.rows[1:, :-1])      # same decisions, same values
     np.testing.assert_allclose(dev.rows[1:, -1], cpu.rows[1:, -1], rtol=RTOL)
+
+
+def test_checkpoint_resume_is_exact_and_widths_can_be_retuned(gpu):
+    torch = gpu["torch"]
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 32, n_frames=2)
+    walkers = 9
+    init = np.tile(p0, (walkers, 1))
+    fo = (np.arange(walkers) % 2).astype(np.int32)
+    kw = dict(seed=4, burn_in=5, thin=3)
+    with gpu["sampler"].GibbsSampler(dom, init, fo, **kw) as a:
+        whole = a.run(90)
+        sa, sta = a.state(), a.stats()
+    with gpu["sampler"].GibbsSampler(dom, init, fo, **kw) as b:
+        first = b.run(40)
+        blob = b.save().clone()
+    with gpu["sampler"].GibbsSampler(dom, init + 1.0, fo, seed=999, burn_in=5, thin=3) as c:   # other start, other seed
+        c.load(blob)
+        assert c.count == 40
+        rest = c.run(50)
+        sc, stc = c.state(), c.stats()
+    assert torch.equal(whole, torch.cat([first, rest], dim=0))
+    for x, y in zip(sa, sc):
+        assert torch.equal(x, y)
+    assert torch.equal(sta["moments"], stc["moments"]) and int(sta["exps"]) == int(stc["exps"])
+    # wider jumps, fewer acceptances: set_widths takes effect for the following runs only
+    from olpefit_b200 import layout
+    w0, _ = layout.default_widths(2)
+    with gpu["sampler"].GibbsSampler(dom, init, fo, seed=4) as s:
+        s.run(200, record=False)
+        acc0 = float(s.stats()["accepts"].sum())
+        s.set_widths(w0 * 8.0)
+        s.run(200, record=False)
+        acc1 = float(s.stats()["accepts"].sum()) - acc0
+    assert acc1 < 0.8 * acc0
+    with pytest.raises(Exception):
+        s2 = gpu["sampler"].GibbsSampler(dom, init, fo, seed=4)
+        try:
+            s2.set_widths(-w0)
+        finally:
+            s2.close()

@@ -2,7 +2,7 @@
 position angle must match a reference CPU run within Monte-Carlo error on the same frame).
 
 The CPU side is tests/golden/posterior_2body_s32.npz, produced by tools/make_posterior_fixture.py:
-64 walkers of the float64 numpy oracle with numpy's Mersenne-Twister stream (the reference's
+64 (2-body) / 48 (3-body) walkers of the float64 numpy oracle with numpy's Mersenne-Twister stream (the reference's
 stream), 50,000 updates each, first 10,000 dropped, every 10th kept.  The GPU side runs the same
 configuration with 2048 walkers on the Philox stream.  Bit-equal chains are impossible by design
 (the reference is unseeded); the comparison is distributional, with standard errors taken from
@@ -19,11 +19,12 @@ HEADER = {"itime": 1.0, "coadds": 1, "multisam": 1, "sampmode": 2}
 QS = [15.865, 50.0, 84.135]
 
 
-def test_separation_and_position_angle_posterior_match_cpu_reference(golden_dir):
+@pytest.mark.parametrize("fixture", ["posterior_2body_s32.npz", "posterior_3body_s32.npz"])
+def test_separation_and_position_angle_posterior_match_cpu_reference(golden_dir, fixture):
     import torch
     from olpefit_b200 import chains, frame, sampler, synth
 
-    z = np.load(os.path.join(golden_dir, "posterior_2body_s32.npz"))
+    z = np.load(os.path.join(golden_dir, fixture))
     size, nbody, epoch = int(z["size"]), int(z["nbody"]), int(z["epoch"])
     ox, oy = (int(v) for v in z["origin"])
     img, _ = synth.make_frame(epoch, nbody, region=(oy, oy + size, ox, ox + size))

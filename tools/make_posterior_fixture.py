@@ -20,7 +20,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 HEADER = {"itime": 1.0, "coadds": 1, "multisam": 1, "sampmode": 2}
-SIZE, NBODY, EPOCH = 32, 2, 0
+SIZE, EPOCH = 32, 0
+NBODY = int(os.environ.get("LAPF_FIXTURE_NBODY", "2"))
 
 
 def setup():
@@ -63,7 +64,7 @@ def main():
     rows = np.array([o[0] for o in out])                     # [walkers, rows, P+1]
     tries = np.array([o[1] for o in out])
     accepts = np.array([o[2] for o in out])
-    sep, pa = orc.separation_pa(rows[..., 0], rows[..., 1], rows[..., 2], rows[..., 3])
+    sep, pa = orc.separation_pa(rows[..., 0], rows[..., 1], rows[..., 2], rows[..., 3])   # star -> first companion
     qs = [15.865, 50.0, 84.135]
     res = {
         "size": SIZE, "nbody": NBODY, "epoch": EPOCH, "p0": p0, "truth": truth, "origin": np.array(origin),
@@ -77,7 +78,7 @@ def main():
         "acceptance": accepts.sum(axis=0) / tries.sum(axis=0),
         "chi2_first_rows": rows[:, :5, -1], "chi2_last_rows": rows[:, -5:, -1],
     }
-    path = os.path.join(ROOT, "tests", "golden", "posterior_2body_s32.npz")
+    path = os.path.join(ROOT, "tests", "golden", "posterior_%dbody_s32.npz" % NBODY)
     np.savez_compressed(path, **res)
     print("wrote", path, os.path.getsize(path), "bytes in %.0f s" % (time.time() - t0))
     print("sep quantiles", res["sep_q"], " SE(median) ~", res["sep_q_walker"][:, 1].std() / np.sqrt(a.walkers))
