@@ -176,7 +176,8 @@ def gelman_rubin_from_moments(moments, n_rows, n_walkers, python2_division=True)
     w = s_var / m
     overall = s_mean / m
     b = (n / (m - 1.0)) * (s_mean2 - m * overall * overall)
-    psrf = (((n - 1.0) / n) * w + ((m + 1.0) / (m * n)) * b) / w
+    with np.errstate(divide="ignore", invalid="ignore"):   # a parameter that never moved has w = 0
+        psrf = (((n - 1.0) / n) * w + ((m + 1.0) / (m * n)) * b) / w
     factor = 1.0 if python2_division else 19.0 / 17.0
     return psrf, np.sqrt(factor * psrf)
 
