@@ -82,6 +82,20 @@ def _cpu_walker(job):
     return time.perf_counter() - t0, res.n_updates
 
 
+def cpu_full_frame(nbody, n_updates):
+    """One host walker on the reference's own pixel domain, the whole 1024 x 1024 frame
+    (apf_step2.py:94,237): seconds per update on one core."""
+    from olpefit_b200 import synth
+    from oracle import lapf_oracle as orc
+    lay = orc.layout_for(nbody)
+    img32, truth = synth.make_frame(0, nbody)
+    img = img32.astype(np.float64)
+    w = orc.weight_map(img, HEADER)
+    t0 = time.perf_counter()
+    orc.run_chain(img, w, lay, truth, orc.NumpyStream(1), n_updates=n_updates, burn_in=0)
+    return (time.perf_counter() - t0) / (n_updates + 1)      # + the initial evaluation
+
+
 def cpu_walkers(nbody, size, n_updates, cores):
     """``cores`` walkers in ``cores`` processes (one process per walker, like one MPI rank per
     walker, apf_step2.py:54-57).  Returns (seconds of the slowest walker, total updates)."""
@@ -185,8 +199,12 @@ def run_b200(a):
         # before CUDA is touched in this process; rank 0 at N=1 only
         cores = os.cpu_count() or 1
         t, n, wall = cpu_walkers(a.nbody, a.stamp, a.cpu_updates, cores)
+        sec_full = cpu_full_frame(a.nbody, 16)
         cpu = {"value": n * a.stamp * a.stamp / t, "unit": UNIT, "cores": cores, "kind": "port",
                "updates_per_sec": n / t, "seconds": round(wall, 2),
+               "full_frame_1024": {"seconds_per_update_one_core": sec_full,
+                                   "pixel_evals_per_sec_one_core": 1024 * 1024 / sec_full,
+                                   "note": "the reference's own domain (whole frame per update), 1 core, 16 updates"},
                "sample": "%d host walkers (one process each, numpy float64 restatement of "
                          "apf_step2.py:300-351) x %d updates on epoch 0, %dx%d stamp"
                          % (cores, a.cpu_updates, a.stamp, a.stamp)}

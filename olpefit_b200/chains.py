@@ -63,16 +63,35 @@ def write_walker_csv(path, rows, leading_nan=True, append=False):
                                                 rows.shape[1], rows.shape[1], flags))
 
 
+_pool = None
+
+
+def _writer_pool():
+    global _pool
+    if _pool is None:
+        import concurrent.futures as cf
+        _pool = cf.ThreadPoolExecutor(max_workers=max(1, min(32, (os.cpu_count() or 1))))
+    return _pool
+
+
 def write_segment_csv(paths, segment, first):
-    """Append a time-major chain segment [rows, W, P+1] to the W per-walker files ``paths``."""
+    """Append a time-major chain segment [rows, W, P+1] to the W per-walker files ``paths``.
+    One file per walker is the reference's layout (apf_step2.py:357); the walkers' files are
+    formatted and written concurrently (the native writer runs outside the GIL)."""
     seg = np.ascontiguousarray(segment, dtype=np.float64)
     nrow, nw, ncol = seg.shape
     lib = _lib.load()
-    flags_first = CSV_LEADING_NAN_ROW
-    for w in range(nw):
-        flags = flags_first if first else CSV_APPEND
+    flags = CSV_LEADING_NAN_ROW if first else CSV_APPEND
+
+    def one(w):
         base = seg.ctypes.data + w * ncol * 8
-        _lib.check(lib.lapf_write_chain_csv(os.fsencode(paths[w]), base, nrow, ncol, nw * ncol, flags))
+        return lib.lapf_write_chain_csv(os.fsencode(paths[w]), base, nrow, ncol, nw * ncol, flags)
+
+    if nw == 1:
+        _lib.check(one(0))
+        return
+    for rc in _writer_pool().map(one, range(nw)):
+        _lib.check(rc)
 
 
 def write_acceptance(path, accepts, tries):

@@ -230,3 +230,24 @@ def test_cli_parsers_keep_reference_flags():
     assert a.n_steps == 5000 and not hasattr(a, "initial_guess_option")
     a = cli._parser("step2_3body").parse_args(["img.a.b.c.fits"])
     assert not hasattr(a, "initial_guess_option")
+
+
+def test_automatic_step1_writes_the_reference_file(tmp_path):
+    """apf_step1.py:145-175 without the clicks: brightest pixel of the 21 x 21 box + 0.5, one line."""
+    import apf_step1_auto
+    from olpefit_b200 import frame, step1, synth
+    img, truth = synth.make_frame(0, 2, hot_pixels=False)
+    path = str(tmp_path / "N2.20090531.29966.LDIF.fits")
+    frame.write_fits(path, img, synth.HEADER)
+    assert apf_step1_auto.main([path, "--star", "509,514", "--companion", "521.7,519.2", "--sky", "100.9,120.2"]) == 0
+    g = np.loadtxt(open(str(tmp_path / "29966_initialguess"), "rb"), delimiter=" ")     # apf_step2.py:262
+    assert g.shape == (6,)
+    iy, ix = np.unravel_index(np.argmax(img[503:524, 498:519]), (21, 21))
+    assert (g[0], g[1]) == (498 + ix + 0.5, 503 + iy + 0.5)
+    assert abs(g[0] - truth[0]) < 1.5 and abs(g[1] - truth[1]) < 1.5
+    assert g[4] == 100 and g[5] == 120
+    raw = step1.initial_guess(img, [(509, 514), (521.7, 519.2)], (100, 120), refine=False)
+    assert raw[:4] == [509.0, 514.0, 521.7, 519.2]
+    # the numbers feed step 2's starting point exactly like the reference's file does
+    p = frame.initial_parameters(img, g, 2)
+    assert p.shape == (16,) and p[6] == img[int(g[1] - 1), int(g[0] - 1)]
