@@ -31,8 +31,10 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
+    # build next to the target and rename: several ranks may decide to rebuild at the same time
+    tmp = "%s.tmp.%d" % (LIB, os.getpid())
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + SOURCES
+           "-shared", "-Xcompiler", "-fPIC", "-o", tmp] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -40,7 +42,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         sys.stderr.write(res.stderr)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -27,3 +27,23 @@ T('run', lambda: smp.run(U, out=chain))
 T('d2h chain %d MB' % (chain_h.numel() * 8 >> 20), lambda: chain_h.copy_(chain, non_blocking=True))
 T('stats', lambda: smp.stats(moments=False))
 print('pinned?', chain_h.is_pinned(), frames_h.is_pinned())
+
+tot_h = torch.empty((2 * P + 2,), dtype=torch.int64).pin_memory()
+def whole():
+    frames_d.copy_(frames_h, non_blocking=True); init_d.copy_(init_h, non_blocking=True)
+    frame.prepare_domain(frames_d, HEADER, origin=origins, nbody=2, into=dom)
+    smp.reset(init_d, seed=3)
+    ch = smp.run(U, out=chain)
+    chain_h.copy_(ch, non_blocking=True)
+    stt = smp.stats(moments=False)
+    tot_h.copy_(torch.cat([stt["tries"], stt["accepts"], stt["min_tries"].reshape(1), stt["exps"].reshape(1)]), non_blocking=True)
+T('whole e2e step', whole, n=8)
+def whole_nosync_prep():
+    frames_d.copy_(frames_h, non_blocking=True); init_d.copy_(init_h, non_blocking=True)
+    t0 = time.perf_counter(); frame.prepare_domain(frames_d, HEADER, origin=origins, nbody=2, into=dom); t1 = time.perf_counter()
+    smp.reset(init_d, seed=3); t2 = time.perf_counter()
+    ch = smp.run(U, out=chain); t3 = time.perf_counter()
+    chain_h.copy_(ch, non_blocking=True); t4 = time.perf_counter()
+    stt = smp.stats(moments=False); t5 = time.perf_counter()
+    print('  host ms: prep %.2f reset %.2f run %.2f d2h-enqueue %.2f stats %.2f' % tuple(1e3 * x for x in (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)))
+whole_nosync_prep(); torch.cuda.synchronize(); whole_nosync_prep(); torch.cuda.synchronize()
