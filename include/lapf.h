@@ -153,9 +153,10 @@ int lapf_sampler_state(lapf_sampler* s, double* state_out, uint32_t* tries_out,
  *               over walkers and parameters of tries (stop rule of apf_step2.py:300, globalised),
  *               then the number of exponentials the sampler really evaluated so far (what is
  *               left of ny*nx*K per update after far-field culling; roofline accounting)
- *   moments_out device double[F][P+1][3] or NULL: per frame and column, over that frame's
- *               walkers: sum of chain means, sum of squared chain means, sum of chain variances
- *               of the rows recorded so far (the ingredients of apf_step3.py:265-276)
+ *   moments_out device double[F][P+1][4] or NULL: per frame and column, over that frame's
+ *               walkers and the rows recorded so far: a reference value r, sum of (chain mean - r),
+ *               sum of (chain mean - r)^2, sum of chain variances -- the ingredients of the
+ *               Gelman-Rubin statistic (apf_step3.py:265-276), centred so nothing cancels
  *   counts_out  device int64[F+1] or NULL: walkers per frame, then rows recorded per walker */
 int lapf_sampler_stats(lapf_sampler* s, int64_t* totals_out, double* moments_out,
                        int64_t* counts_out, void* stream);

@@ -187,11 +187,12 @@ def gelman_rubin(chains, python2_division=True):
 
 def gelman_rubin_from_moments(moments, n_rows, n_walkers, python2_division=True):
     """The same statistic from the device-reduced sufficient statistics of ``lapf_sampler_stats``:
-    moments[..., 0] = sum of chain means, [..., 1] = sum of squared chain means, [..., 2] = sum of
-    chain variances.  Equal-length chains make the overall mean the mean of the chain means."""
+    moments[..., 0] = reference value r, [..., 1] = sum of (chain mean - r), [..., 2] = sum of
+    (chain mean - r)^2, [..., 3] = sum of chain variances.  Equal-length chains make the overall
+    mean the mean of the chain means."""
     mom = np.asarray(moments, dtype=np.float64)
     n, m = float(n_rows), np.asarray(n_walkers, dtype=np.float64)
-    s_mean, s_mean2, s_var = mom[..., 0], mom[..., 1], mom[..., 2]
+    s_mean, s_mean2, s_var = mom[..., 1], mom[..., 2], mom[..., 3]
     w = s_var / m
     overall = s_mean / m
     b = (n / (m - 1.0)) * (s_mean2 - m * overall * overall)

@@ -479,12 +479,16 @@ __global__ void totals_init_kernel(unsigned long long* out, int P) {
 }
 
 // One CTA per frame, one warp per column: fixed-order FP64 reduction over that frame's walkers.
+// Chain means are taken relative to a per-frame reference value (the first walker's starting
+// point) so that the between-chain sum of squares does not cancel for parameters with a large
+// mean and a tiny spread (positions: ~512 +- 0.003).
 __global__ void moments_kernel(const double* __restrict__ moments, const double* __restrict__ shift,
                                const int32_t* __restrict__ walker_of, const int32_t* __restrict__ frame_start,
-                               int P, int64_t n_rows, double* __restrict__ out /*[F][P+1][3]*/) {
+                               int P, int64_t n_rows, double* __restrict__ out /*[F][P+1][4]*/) {
     const int f = blockIdx.x, col = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (col > P) return;
     const int b = frame_start[f], e = frame_start[f + 1];
+    const double ref = (e > b) ? shift[(size_t)walker_of[b] * (P + 1) + col] : 0.0;
     double s_mean = 0.0, s_mean2 = 0.0, s_var = 0.0;
     if (n_rows > 0) {
         const double inv = 1.0 / (double)n_rows;
@@ -492,7 +496,7 @@ __global__ void moments_kernel(const double* __restrict__ moments, const double*
             const size_t w = (size_t)walker_of[i];
             const double m1 = moments[(w * (P + 1) + col) * 2] * inv;
             const double m2 = moments[(w * (P + 1) + col) * 2 + 1] * inv;
-            const double mean = shift[w * (P + 1) + col] + m1;
+            const double mean = (shift[w * (P + 1) + col] - ref) + m1;
             s_mean += mean;
             s_mean2 += mean * mean;
             s_var += m2 - m1 * m1;     // population variance, np.std()**2 of apf_step3.py:270
@@ -502,10 +506,11 @@ __global__ void moments_kernel(const double* __restrict__ moments, const double*
     s_mean2 = warp_sum_f64(s_mean2);
     s_var = warp_sum_f64(s_var);
     if (lane == 0) {
-        double* o = out + ((size_t)f * (P + 1) + col) * 3;
-        o[0] = s_mean;
-        o[1] = s_mean2;
-        o[2] = s_var;
+        double* o = out + ((size_t)f * (P + 1) + col) * 4;
+        o[0] = ref;
+        o[1] = s_mean;
+        o[2] = s_mean2;
+        o[3] = s_var;
     }
 }
 

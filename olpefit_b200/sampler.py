@@ -147,11 +147,12 @@ class GibbsSampler:
     def stats(self, moments=True):
         """Batch statistics reduced on the device (K4).  Returns a dict of device tensors:
         tries[P], accepts[P], min_tries (scalar), exps (scalar: exponentials really evaluated),
-        moments [F, P+1, 3], walkers_per_frame [F], rows (scalar)."""
+        moments [F, P+1, 4] (reference, sum of centred chain means, of their squares, of chain
+        variances), walkers_per_frame [F], rows (scalar)."""
         dev = self.domain.device
         pn, nf = self.nparam, self.domain.n_frames
         tot = torch.empty((2 * pn + 2,), dtype=torch.int64, device=dev)
-        mom = torch.empty((nf, pn + 1, 3), dtype=torch.float64, device=dev) if moments else None
+        mom = torch.empty((nf, pn + 1, 4), dtype=torch.float64, device=dev) if moments else None
         cnt = torch.empty((nf + 1,), dtype=torch.int64, device=dev)
         _lib.check(self.lib.lapf_sampler_stats(self._h, tot.data_ptr(),
                                                mom.data_ptr() if mom is not None else None,

@@ -290,10 +290,11 @@ def test_sampler_moments_match_chain(gpu):
     assert st["walkers_per_frame"].cpu().numpy().tolist() == [10, 10]
     for f in range(2):
         sub = chain[:, frame_of == f, :]                       # [rows, walkers_f, P+1]
-        means = sub.mean(axis=0)
-        np.testing.assert_allclose(mom[f, :, 0], means.sum(axis=0), rtol=1e-10)
-        np.testing.assert_allclose(mom[f, :, 1], (means ** 2).sum(axis=0), rtol=1e-10)
-        np.testing.assert_allclose(mom[f, :, 2], (sub.std(axis=0) ** 2).sum(axis=0), rtol=1e-6, atol=1e-12)
+        means = sub.mean(axis=0) - mom[f, :, 0]                # centred on the per-frame reference
+        np.testing.assert_allclose(mom[f, :-1, 0], p0)         # ... which is the starting point here
+        np.testing.assert_allclose(mom[f, :-1, 1], means.sum(axis=0)[:-1], rtol=1e-7, atol=1e-12)
+        np.testing.assert_allclose(mom[f, :-1, 2], (means ** 2).sum(axis=0)[:-1], rtol=1e-7, atol=1e-14)
+        np.testing.assert_allclose(mom[f, :, 3], (sub.std(axis=0) ** 2).sum(axis=0), rtol=1e-6, atol=1e-12)
 
 
 def test_team_mode_agrees_with_single_warp_mode(gpu):

@@ -174,7 +174,8 @@ def test_gelman_rubin_from_device_moments_equals_direct():
     rng = np.random.default_rng(4)
     x = 3.0 + rng.normal(size=(200, 7)) * 0.1 + rng.normal(size=(1, 7)) * 0.05
     means = x.mean(axis=0)
-    mom = np.array([means.sum(), (means ** 2).sum(), x.var(axis=0).sum()])
+    ref = x[0, 0]
+    mom = np.array([ref, (means - ref).sum(), ((means - ref) ** 2).sum(), x.var(axis=0).sum()])
     psrf, rc = chains.gelman_rubin_from_moments(mom, 200, 7)
     psrf_d, rc_d = chains.gelman_rubin(x)
     assert psrf == pytest.approx(psrf_d, rel=1e-9) and rc == pytest.approx(rc_d, rel=1e-9)
