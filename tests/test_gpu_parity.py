@@ -515,3 +515,37 @@ def test_checkpoint_resume_is_exact_and_widths_can_be_retuned(gpu):
             s2.set_widths(-w0)
         finally:
             s2.close()
+
+
+def test_error_paths_on_device(gpu):
+    """Bad arguments are refused with a message, before anything is launched."""
+    torch = gpu["torch"]
+    from olpefit_b200 import _lib
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 32, n_frames=2)
+    S = gpu["sampler"].GibbsSampler
+    with pytest.raises(_lib.LapfError, match="frame_of"):
+        S(dom, np.tile(p0, (3, 1)), np.array([0, 1, 2], dtype=np.int32))          # frame 2 does not exist
+    with pytest.raises(_lib.LapfError, match="thin"):
+        S(dom, p0[None], thin=0)
+    with pytest.raises(_lib.LapfError, match="team_warps"):
+        S(dom, p0[None], team_warps=3)
+    with pytest.raises(_lib.LapfError, match="team_warps"):
+        S(dom, p0[None], team_warps=16)                                            # 32-pixel stamps: 4 row steps
+    img, _ = gpu["synth"].make_frame(0, 2, region=(480, 530, 470, 547))
+    ragged = gpu["frame"].prepare_domain(img, HEADER, origin=(470, 480), nbody=2)
+    with pytest.raises(_lib.LapfError, match="square stamps"):
+        S(ragged, p0[None])                                                        # K1 handles it, the sampler does not
+    with S(dom, np.tile(p0, (4, 1))) as s:
+        small = torch.empty((2, 4, 17), dtype=torch.float64, device="cuda")
+        with pytest.raises(ValueError):
+            s.run(10, out=small)
+        assert _lib.load().lapf_sampler_run(s._h, 10, small.data_ptr(), 2, None) == -1
+        assert b"rows" in _lib.load().lapf_last_error()
+        assert _lib.load().lapf_sampler_run(s._h, -1, None, 0, None) == -1
+        assert s.count == 0                                                         # nothing ran
+        with pytest.raises(_lib.LapfError, match="too small"):
+            _lib.check(_lib.load().lapf_sampler_load(s._h, small.data_ptr(), 16, None))
+    # out-of-range frame index in the stateless operator: nan for that vector only
+    _, c = dom.model_chi2(np.stack([p0, p0, p0]), frame_of=np.array([0, 7, 1], dtype=np.int32))
+    c = c.cpu().numpy()
+    assert np.isfinite(c[0]) and np.isnan(c[1]) and np.isfinite(c[2])
