@@ -113,8 +113,8 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
     load_centres_amps<NB>(cf, tf[warp], pr.floor_index);
     load_shape<NB>(cf, 0, tf[warp]);
     load_shape<NB>(cf, 1, tf[warp]);
-    __shared__ __align__(16) float rt[4][NY * 4 * NB];
-    build_row_table<NB, NY>(rt[warp], cf, lane);
+    __shared__ __align__(16) float rt[4][Rows<NY>::TR * Tab<NB>::RS];
+    set_fast<NB, NX, NY>(cf, lane);
     if (NX >= 64 && pr.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
     const size_t off = (size_t)f * NX * NY;
     double chi = warp_chi2<NB, NX, NY, STORE, false>(cf, rt[warp], pr.data + off, pr.weight + off,
@@ -333,7 +333,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
                 set_shape_sc<NB>(cf, 0, ws.tf[L::I_SX], ws.tf[L::I_SY], tsin, tcos);
             }
         }
-        build_row_table<NB, NY>(rt, cf, lane);
+        set_fast<NB, NX, NY>(cf, lane);
         // in a team the update time is set by the warp with the busiest rows: culling cannot help there
         if (NX >= 64 && TEAM == 1 && a.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
         unsigned e_upd = 0;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
     __shared__ uint64_t bar;
     float* sd = reinterpret_cast<float*>(smem_raw);
     float* sw = sd + NX * NY;
-    float* rt = sw + NX * NY;                       // [NW][NY][4*NB] row tables
+    float* rt = sw + NX * NY;                       // [NW][TR][Tab::RS] row tables
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
         }
         const int team = warp / TEAM, tw = warp % TEAM;
         if (team < a.item_count[it])
-            run_walker<NB, NX, NY, TEAM>(a, sd, sw, scratch[warp], rt + warp * (NY * 4 * NB), team_part[team],
+            run_walker<NB, NX, NY, TEAM>(a, sd, sw, scratch[warp], rt + warp * (Rows<NY>::TR * Tab<NB>::RS), team_part[team],
                                          team, tw, a.walker_of[a.item_first[it] + team], f, lane);
     }
 }
@@ -758,7 +758,7 @@ static int configure_gibbs(lapf_sampler* s) {
     auto kern = gibbs_kernel<NB, NX, NX, NW, MINB, TEAM>;
     s->nw = NW / TEAM;   // walkers per CTA item
     s->minb = MINB;
-    s->smem = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * NX * 4 * NB;
+    s->smem = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * Rows<NX>::TR * Tab<NB>::RS;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, s->smem));

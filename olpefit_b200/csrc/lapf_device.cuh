@@ -111,6 +111,8 @@ struct Coef {
     // (class 0 = narrow cores, 1 = wide wings; empty when lo > hi), and the column panels (bit p)
     int lo[2], hi[2];
     uint32_t pan[2];
+    // the factorised pixel loop (row_steps_fast) is safe for this vector (set_fast)
+    bool fast;
 };
 
 // a, b, c of astropy Gaussian2D.evaluate, pre-scaled so that the
@@ -201,51 +203,82 @@ struct Geo {
     static_assert(NX % PW == 0 && (NX == 32 || NX % 64 == 0), "unsupported stamp width");
 };
 
-// Row table: the row-dependent part of every exponent, computed ONCE per proposal by the warp
-// (row r by lane r mod 32) instead of once per row step by every lane:
-//   rt[r][k]     = sb_k * dy        rt[r][K + k] = sc_k * dy^2,      dy = r - y0_k
-// so that per pixel and component  q = fma(dx, fma(sa_k, dx, rt[r][k]), rt[r][K+k]).
-// The four row groups of a warp read four consecutive rows: one conflict-free wavefront per load.
-template <int NB, int NY>
-__device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Coef<NB>& cf, int lane) {
+// Row table: everything that depends on the row only, computed ONCE per proposal by the warp
+// (row r by lane r mod 32) instead of once per row step by every lane.  One entry of Tab::RS floats
+// per row:
+//   [2k], [2k+1]         sb_k * dy_k,  sc_k * dy_k^2     (dy_k = r - y0_k), for component k < K
+//   [2K + 4c .. +3]      2^(j h) for j = -3, -1, 1, 3,  h = sb_c * (r - y0_c) / 2, for shape class c
+// The first pair gives the exponent of component k at any column of the row:
+//   q = fma(dx, fma(sa, dx, sb*dy), sc*dy^2);
+// the second the factor that moves it half a pixel / one and a half pixels left or right of an
+// anchor column (see row_steps_fast).  y0_c is the centre of the class's FIRST component; the
+// other components of the class fold their offset into the lane constants.
+// A table covers TR = min(NY, 64) rows; 128-pixel stamps are walked as two halves.  The entry is
+// padded to 20 floats so the 4 (or 8) row groups of a warp read distinct banks.
+template <int NB>
+struct Tab {
+    static constexpr int K = 2 * NB;
+    static constexpr int RS = 20;
+    static constexpr int OFF_R = 2 * K;
+    static_assert(OFF_R + 8 <= RS, "row table entry too small");
+};
+
+template <int NY>
+struct Rows {
+    static constexpr int TR = NY < 64 ? NY : 64;   // rows per table
+    static constexpr int HALVES = NY / TR;
+    static_assert(NY % TR == 0 && TR % 32 == 0, "unsupported stamp height");
+};
+
+template <int NB, int TR>
+__device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Coef<NB>& cf, int lane, int row0) {
     constexpr int K = 2 * NB;
-    static_assert(NY % 32 == 0, "row table is built 32 rows at a time");
+    using T = Tab<NB>;
     __syncwarp();   // readers of the previous table are done
-    if (NY % 64 == 0) {
+    if (TR == 64) {
         // two rows (r, r+32) per pass, as the two halves of packed FP32 operations
+        const float2 fr = make_float2((float)(row0 + lane), (float)(row0 + 32 + lane));
+        float4* o0 = reinterpret_cast<float4*>(rt + lane * T::RS);
+        float4* o1 = reinterpret_cast<float4*>(rt + (32 + lane) * T::RS);
+        float2 v[2 * K];
 #pragma unroll
-        for (int r0 = 0; r0 < NY; r0 += 64) {
-            const float2 fr = make_float2((float)(r0 + lane), (float)(r0 + 32 + lane));
-            float2 v[2 * K];
+        for (int k = 0; k < K; ++k) {
+            const float2 yd = __fadd2_rn(fr, make_float2(-cf.y0[k], -cf.y0[k]));
+            const float2 sc2 = make_float2(cf.sc[k & 1], cf.sc[k & 1]);
+            v[2 * k] = __fmul2_rn(make_float2(cf.sb[k & 1], cf.sb[k & 1]), yd);
+            v[2 * k + 1] = __fmul2_rn(__fmul2_rn(sc2, yd), yd);
+        }
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const float2 yd = __fadd2_rn(fr, make_float2(-cf.y0[k], -cf.y0[k]));
-                const float2 sc2 = make_float2(cf.sc[k & 1], cf.sc[k & 1]);
-                v[k] = __fmul2_rn(make_float2(cf.sb[k & 1], cf.sb[k & 1]), yd);
-                v[K + k] = __fmul2_rn(__fmul2_rn(sc2, yd), yd);
-            }
-            float4* o0 = reinterpret_cast<float4*>(rt + (r0 + lane) * 2 * K);
-            float4* o1 = reinterpret_cast<float4*>(rt + (r0 + 32 + lane) * 2 * K);
+        for (int q = 0; q < 2 * K / 4; ++q) {
+            o0[q] = make_float4(v[4 * q].x, v[4 * q + 1].x, v[4 * q + 2].x, v[4 * q + 3].x);
+            o1[q] = make_float4(v[4 * q].y, v[4 * q + 1].y, v[4 * q + 2].y, v[4 * q + 3].y);
+        }
 #pragma unroll
-            for (int q = 0; q < 2 * K / 4; ++q) {
-                o0[q] = make_float4(v[4 * q].x, v[4 * q + 1].x, v[4 * q + 2].x, v[4 * q + 3].x);
-                o1[q] = make_float4(v[4 * q].y, v[4 * q + 1].y, v[4 * q + 2].y, v[4 * q + 3].y);
-            }
+        for (int c = 0; c < 2; ++c) {
+            const float2 h = __fmul2_rn(v[2 * c], make_float2(0.5f, 0.5f));     // sb_c * dy_c / 2
+            const float2 h3 = __fmul2_rn(v[2 * c], make_float2(1.5f, 1.5f));
+            o0[T::OFF_R / 4 + c] = make_float4(ex2_approx(-h3.x), ex2_approx(-h.x), ex2_approx(h.x), ex2_approx(h3.x));
+            o1[T::OFF_R / 4 + c] = make_float4(ex2_approx(-h3.y), ex2_approx(-h.y), ex2_approx(h.y), ex2_approx(h3.y));
         }
     } else {
 #pragma unroll
-        for (int r0 = 0; r0 < NY; r0 += 32) {
-            const float fr = (float)(r0 + lane);
+        for (int r0 = 0; r0 < TR; r0 += 32) {
+            const float fr = (float)(row0 + r0 + lane);
+            float4* o = reinterpret_cast<float4*>(rt + (r0 + lane) * T::RS);
             float v[2 * K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const float yd = fr - cf.y0[k];
-                v[k] = cf.sb[k & 1] * yd;
-                v[K + k] = (cf.sc[k & 1] * yd) * yd;
+                v[2 * k] = cf.sb[k & 1] * yd;
+                v[2 * k + 1] = (cf.sc[k & 1] * yd) * yd;
             }
-            float4* o = reinterpret_cast<float4*>(rt + (r0 + lane) * 2 * K);
 #pragma unroll
             for (int q = 0; q < 2 * K / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float h = v[2 * c] * 0.5f, h3 = v[2 * c] * 1.5f;
+                o[T::OFF_R / 4 + c] = make_float4(ex2_approx(-h3), ex2_approx(-h), ex2_approx(h), ex2_approx(h3));
+            }
         }
     }
     __syncwarp();
@@ -276,7 +309,7 @@ __device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
     const int sh = lane & 1;
     const float sa = sh ? cf.sa[1] : cf.sa[0], sb = sh ? cf.sb[1] : cf.sb[0], sc = sh ? cf.sc[1] : cf.sc[0];
     // approximate log2 / divide / sqrt are fine here: the radius gets a whole pixel of slack
-    const float tau = 0x1p-25f * fabsf(cf.floor);
+    const float tau = 0x1p-27f * fabsf(cf.floor);
     const float L = __log2f(__fdividef(fabsf(a), tau));    // bits of headroom above tau
     int lo = 0, hi = STEPS - 1;                            // default: everything (also for nan / inf)
     uint32_t pm = kAllPans;
@@ -319,16 +352,37 @@ __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
     for (int c = 0; c < 2; ++c) { cf.lo[c] = 0; cf.hi[c] = NY / Geo<NX>::RG - 1; cf.pan[c] = 0xffffffffu; }
 }
 
+// The factorised pixel loop multiplies factors whose exponents can be large although their sum is
+// not.  It is used only when, for every pixel of the stamp, the column factor's exponent
+// |j (sa (2 dxa + j) + w_k)| and the row factor's |1.5 sb dy| stay below 40 -- no factor overflows
+// or underflows on its own -- and when an anchor exponential that underflows (q0 < -126) implies
+// that its four pixels are below 2^-46 |A| <= 2^-25 |floor|.  Anything else, nan and inf included,
+// takes the plain loop (one exponential per pixel and component).  The decision is a function of
+// the coefficients only and is the same in every lane.
+template <int NB, int NX, int NY>
+__device__ __forceinline__ void set_fast(Coef<NB>& cf, int lane) {
+    constexpr int K = 2 * NB;
+    float a = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k)
+        if (lane == k) { a = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
+    const int sh = lane & 1;
+    const float sa = sh ? cf.sa[1] : cf.sa[0], sb = sh ? cf.sb[1] : cf.sb[0], sc = sh ? cf.sc[1] : cf.sc[0];
+    const float yref = sh ? cf.y0[1] : cf.y0[0];
+    const float dxm = fabsf(x0 - 0.5f * NX) + 0.5f * NX;      // >= |anchor - x0| for every anchor column
+    const float argc = 1.5f * (fabsf(sa) * (2.f * dxm + 1.5f) + fabsf(sb * (yref - y0)));
+    const float argr = 1.5f * fabsf(sb) * (fabsf(yref - 0.5f * NY) + 0.5f * NY);
+    const bool ok = argc <= 40.f && argr <= 40.f && fabsf(sc) <= 1e30f &&
+                    fabsf(a) <= 0x1p21f * fabsf(cf.floor) && fabsf(a) <= 1e12f;    // all false on nan
+    cf.fast = __all_sync(kFull, ok || lane >= K);
+}
+
 // Row steps [i0, i1) of one panel for the component classes KIND says (0: none, the model is the
 // floor; 1: wide wings only; 2: all components).  chi-square terms are added to the four FP32
-// accumulators s0, s1 in row order, whatever the segmentation (so culling does not regroup sums).  PREP = true: the planes hold d*sqrt(w) and -sqrt(w) (the sampler converts a stamp
-// once after staging it); PREP = false: raw data / weight planes, converted per pixel.  Both give
+// accumulators s0, s1 in row order, whatever the segmentation (so culling does not regroup sums).
+// PREP = true: the planes hold d*sqrt(w) and -sqrt(w) (the sampler converts a stamp once after
+// staging it); PREP = false: raw data / weight planes, converted per pixel.  Both give
 // bit-identical chi-square: the residual is always  r = fma(-sqrt(w), m, d*sqrt(w)),  chi2 += r*r.
-//
-// Arithmetic is issued as packed FFMA2 (fma.rn.f32x2, new on sm_100): two adjacent pixels per
-// instruction, scalar coefficients as broadcast operands.  Per pixel PAIR and component that is
-// 3 FFMA2 + 2 MUFU.EX2, which keeps the issue slots needed per MUFU below the SFU's own rate
-// (measured: a MUFU costs ~4 issue cycles), so the loop is SFU-bound.
 struct StepPtrs {          // where the next row step of this lane lives
     const float* rp;       // row table
     const float* dp;       // data plane
@@ -336,10 +390,45 @@ struct StepPtrs {          // where the next row step of this lane lives
     float* mp;             // model output (STORE only)
 };
 
+// model of 8 pixels -> (optional store) -> residuals -> chi-square accumulators
+template <int NX, bool STORE, bool PREP>
+__device__ __forceinline__ void finish_step(const float2 (&m)[4], const float4& dA, const float4& dB,
+                                            const float4& wA, const float4& wB, float* mp, int colA, int colB,
+                                            float2& s0, float2& s1) {
+    if (STORE) {
+        *reinterpret_cast<float4*>(mp + colA) = make_float4(m[0].x, m[0].y, m[1].x, m[1].y);
+        *reinterpret_cast<float4*>(mp + colB) = make_float4(m[2].x, m[2].y, m[3].x, m[3].y);
+    }
+    float2 dv[4] = {make_float2(dA.x, dA.y), make_float2(dA.z, dA.w), make_float2(dB.x, dB.y),
+                    make_float2(dB.z, dB.w)};
+    float2 wv[4] = {make_float2(wA.x, wA.y), make_float2(wA.z, wA.w), make_float2(wB.x, wB.y),
+                    make_float2(wB.z, wB.w)};
+    if (!PREP) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float rx = sqrtf(wv[j].x), ry = sqrtf(wv[j].y);
+            dv[j] = make_float2(dv[j].x * rx, dv[j].y * ry);
+            wv[j] = make_float2(-rx, -ry);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float2 ra = __ffma2_rn(wv[j], m[j], dv[j]);
+        const float2 rb = __ffma2_rn(wv[2 + j], m[2 + j], dv[2 + j]);
+        s0 = __ffma2_rn(ra, ra, s0);
+        s1 = __ffma2_rn(rb, rb, s1);
+    }
+}
+
+// ---- plain loop: one exponential per pixel and component -------------------------------------
+// Arithmetic is issued as packed FFMA2 (fma.rn.f32x2, new on sm_100): two adjacent pixels per
+// instruction, scalar coefficients as broadcast operands.  Per pixel PAIR and component that is
+// 3 FFMA2 + 2 MUFU.EX2: SFU-bound.  Kept for parameter vectors set_fast turns away.
 template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND>
 __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)[2 * NB][4], float2& s0, float2& s1,
                                           int& i, int i1, StepPtrs& sp, int colA, int colB) {
     using G = Geo<NX>;
+    using T = Tab<NB>;
     constexpr int K = 2 * NB;
     const float* rp = sp.rp;
     const float* dp = sp.dp;
@@ -364,8 +453,8 @@ __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)
 #pragma unroll
             for (int k = (KIND == 2 ? 0 : 1); k < K; k += (KIND == 2 ? 1 : 2)) {
                 const float2 sa2 = make_float2(cf.sa[k & 1], cf.sa[k & 1]);
-                const float2 by2 = make_float2(rc[k], rc[k]);
-                const float2 cy2 = make_float2(rc[K + k], rc[K + k]);
+                const float2 by2 = make_float2(rc[2 * k], rc[2 * k]);
+                const float2 cy2 = make_float2(rc[2 * k + 1], rc[2 * k + 1]);
                 const float2 am2 = make_float2(cf.amp[k], cf.amp[k]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -376,31 +465,113 @@ __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)
                 }
             }
         }
-        if (STORE) {
-            *reinterpret_cast<float4*>(mp + colA) = make_float4(m[0].x, m[0].y, m[1].x, m[1].y);
-            *reinterpret_cast<float4*>(mp + colB) = make_float4(m[2].x, m[2].y, m[3].x, m[3].y);
-            mp += G::RG * NX;
-        }
-        float2 dv[4] = {make_float2(dA.x, dA.y), make_float2(dA.z, dA.w), make_float2(dB.x, dB.y),
-                        make_float2(dB.z, dB.w)};
-        float2 wv[4] = {make_float2(wA.x, wA.y), make_float2(wA.z, wA.w), make_float2(wB.x, wB.y),
-                        make_float2(wB.z, wB.w)};
-        if (!PREP) {
+        finish_step<NX, STORE, PREP>(m, dA, dB, wA, wB, mp, colA, colB, s0, s1);
+        if (STORE) mp += G::RG * NX;
+        rp += G::RG * T::RS;
+        dp += G::RG * NX;
+        wp += G::RG * NX;
+    }
+    sp.rp = rp; sp.dp = dp; sp.wp = wp; sp.mp = mp;
+}
+
+// ---- factorised loop -------------------------------------------------------------------------
+// A lane's 8 columns are two groups of 4 adjacent pixels.  With the anchor xa at the centre of a
+// group (between its 2nd and 3rd pixel) and j in {-1.5, -0.5, 0.5, 1.5},
+//     q_k(xa + j, r) = q_k(xa, r) + j (sa (2 dxa_k + j)) + j sb dy_k,        dxa_k = xa - x0_k,
+// and dy_k = (r - y0_c) + (y0_c - y0_k) with c the first component of k's shape class, so
+//     A_k 2^q_k(xa + j, r) = E_k(r) * C_kj * R_cj(r)
+//     E_k(r)  = 2^q_k(xa, r)                         one MUFU.EX2 per GROUP and component
+//     C_kj    = A_k 2^(j (sa (2 dxa_k + j) + sb (y0_c - y0_k)))    lane constant (registers)
+//     R_cj(r) = 2^(j sb (r - y0_c))                  row table, shared by the class
+// and a class adds  R_cj * sum_k C_kj E_k  to the pixel: per pixel pair NB + 1 packed operations
+// for NB components, plus 2 FFMA2 + 2 MUFU per component for the two anchors.  A row step of
+// 8 pixels x 4 components is 40 packed FP32 instructions and 8 MUFU (plain loop: 56 and 32):
+// the loop is bound by the FP32 pipe, not the SFU.
+template <int NB>
+struct LaneK {
+    static constexpr int K = 2 * NB;
+    float2 dxa[K];       // (group A, group B) anchor offset to the centre of component k
+    float2 C[K][4];      // pixel pairs A(-1.5,-0.5) A(0.5,1.5) B(-1.5,-0.5) B(0.5,1.5)
+};
+
+template <int NB>
+__device__ __forceinline__ void lane_consts(LaneK<NB>& lk, const Coef<NB>& cf, float xaA, float xaB) {
+    constexpr int K = 2 * NB;
+    const float2 jlo = make_float2(-1.5f, -0.5f), jhi = make_float2(0.5f, 1.5f);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float rx = sqrtf(wv[j].x), ry = sqrtf(wv[j].y);
-                dv[j] = make_float2(dv[j].x * rx, dv[j].y * ry);
-                wv[j] = make_float2(-rx, -ry);
+    for (int k = 0; k < K; ++k) {
+        const int c = k & 1;
+        const float wk = (k < 2) ? 0.f : cf.sb[c] * (cf.y0[c] - cf.y0[k]);
+        const float2 w2 = make_float2(wk, wk), sa2 = make_float2(cf.sa[c], cf.sa[c]);
+        const float2 am = make_float2(cf.amp[k], cf.amp[k]);
+        lk.dxa[k] = make_float2(xaA - cf.x0[k], xaB - cf.x0[k]);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const float d2 = 2.f * (g ? lk.dxa[k].y : lk.dxa[k].x);
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const float2 jj = p ? jhi : jlo;
+                const float2 arg = __fmul2_rn(jj, __ffma2_rn(sa2, __fadd2_rn(make_float2(d2, d2), jj), w2));
+                lk.C[k][2 * g + p] = __fmul2_rn(am, make_float2(ex2_approx(arg.x), ex2_approx(arg.y)));
             }
         }
+    }
+}
+
+template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND>
+__device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<NB>& lk, float2& s0, float2& s1,
+                                               int& i, int i1, StepPtrs& sp, int colA, int colB) {
+    using G = Geo<NX>;
+    using T = Tab<NB>;
+    constexpr int K = 2 * NB;
+    const float* rp = sp.rp;
+    const float* dp = sp.dp;
+    const float* wp = sp.wp;
+    float* mp = sp.mp;
+#pragma unroll 1
+    for (; i < i1; ++i) {
+        const float4 dA = *reinterpret_cast<const float4*>(dp + colA);
+        const float4 dB = *reinterpret_cast<const float4*>(dp + colB);
+        const float4 wA = *reinterpret_cast<const float4*>(wp + colA);
+        const float4 wB = *reinterpret_cast<const float4*>(wp + colB);
+        float2 m[4];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float2 ra = __ffma2_rn(wv[j], m[j], dv[j]);
-            const float2 rb = __ffma2_rn(wv[2 + j], m[2 + j], dv[2 + j]);
-            s0 = __ffma2_rn(ra, ra, s0);
-            s1 = __ffma2_rn(rb, rb, s1);
+        for (int j = 0; j < 4; ++j) m[j] = make_float2(cf.floor, cf.floor);
+        if (KIND > 0) {
+            float rc[2 * K];
+#pragma unroll
+            for (int q = 0; q < 2 * K / 4; ++q) {
+                const float4 t4 = reinterpret_cast<const float4*>(rp)[q];
+                rc[4 * q] = t4.x; rc[4 * q + 1] = t4.y; rc[4 * q + 2] = t4.z; rc[4 * q + 3] = t4.w;
+            }
+#pragma unroll
+            for (int c = (KIND == 2 ? 0 : 1); c < 2; ++c) {
+                const float4 R = reinterpret_cast<const float4*>(rp + T::OFF_R)[c];
+                const float2 R01 = make_float2(R.x, R.y), R23 = make_float2(R.z, R.w);
+                const float2 sa2 = make_float2(cf.sa[c], cf.sa[c]);
+                float2 u[4];
+#pragma unroll
+                for (int o = 0; o < NB; ++o) {
+                    const int k = 2 * o + c;
+                    const float2 t = __ffma2_rn(sa2, lk.dxa[k], make_float2(rc[2 * k], rc[2 * k]));
+                    const float2 q = __ffma2_rn(lk.dxa[k], t, make_float2(rc[2 * k + 1], rc[2 * k + 1]));
+                    const float eA = ex2_approx(q.x), eB = ex2_approx(q.y);
+                    const float2 ea = make_float2(eA, eA), eb = make_float2(eB, eB);
+                    if (o == 0) {
+                        u[0] = __fmul2_rn(lk.C[k][0], ea); u[1] = __fmul2_rn(lk.C[k][1], ea);
+                        u[2] = __fmul2_rn(lk.C[k][2], eb); u[3] = __fmul2_rn(lk.C[k][3], eb);
+                    } else {
+                        u[0] = __ffma2_rn(lk.C[k][0], ea, u[0]); u[1] = __ffma2_rn(lk.C[k][1], ea, u[1]);
+                        u[2] = __ffma2_rn(lk.C[k][2], eb, u[2]); u[3] = __ffma2_rn(lk.C[k][3], eb, u[3]);
+                    }
+                }
+                m[0] = __ffma2_rn(R01, u[0], m[0]); m[1] = __ffma2_rn(R23, u[1], m[1]);
+                m[2] = __ffma2_rn(R01, u[2], m[2]); m[3] = __ffma2_rn(R23, u[3], m[3]);
+            }
         }
-        rp += G::RG * 2 * K;
+        finish_step<NX, STORE, PREP>(m, dA, dB, wA, wB, mp, colA, colB, s0, s1);
+        if (STORE) mp += G::RG * NX;
+        rp += G::RG * T::RS;
         dp += G::RG * NX;
         wp += G::RG * NX;
     }
@@ -409,73 +580,99 @@ __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)
 
 // chi-square of one parameter vector over the stamp by ONE warp (TEAM = 1), or this warp's share
 // of it (TEAM > 1: warp `tw` takes every TEAM-th row step; the caller adds the partials in a fixed
-// order).
+// order).  Builds the row table(s) in `rt` itself.  `exps` counts the component evaluations
+// (pixels x components) the far-field culling left to do.
 template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1>
-__device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, const float* __restrict__ rt,
+__device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restrict__ rt,
                                             const float* __restrict__ d, const float* __restrict__ w,
                                             float* __restrict__ model_out, int lane, int tw = 0,
                                             unsigned* exps = nullptr) {
     using G = Geo<NX>;
+    using T = Tab<NB>;
     constexpr int K = 2 * NB;
-    constexpr int STEPS = NY / G::RG;            // row steps per panel
-    static_assert(NY % G::RG == 0, "unsupported stamp height");
+    constexpr int TR = Rows<NY>::TR;
+    constexpr int STEPS = TR / G::RG;            // row steps per table (per panel)
+    static_assert(TR % G::RG == 0, "unsupported stamp height");
     static_assert(STEPS % TEAM == 0, "team size must divide the row steps");
     const int c = lane % G::LPR, g = lane / G::LPR;
     const int swap = (G::PW == 32) ? (g & 1) : 0;
     double acc = 0.0;
 #pragma unroll 1
-    for (int pan = 0; pan < G::PANELS; ++pan) {
-        const int colA = pan * G::PW + 4 * c + (G::PW / 2) * swap;
-        const int colB = pan * G::PW + 4 * c + (G::PW / 2) * (1 - swap);
-        float2 xd[K][4];   // pixel pairs: (0,1) (2,3) of group A, (0,1) (2,3) of group B
-        {
-            const float fa = (float)colA, fb = (float)colB;
-            const float2 cols[4] = {make_float2(fa, fa + 1.f), make_float2(fa + 2.f, fa + 3.f),
-                                    make_float2(fb, fb + 1.f), make_float2(fb + 2.f, fb + 3.f)};
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const float2 nx0 = make_float2(-cf.x0[k], -cf.x0[k]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xd[k][j] = __fadd2_rn(cols[j], nx0);
-            }
-        }
-        // segments of this panel: [0,wlo) none, [wlo,nlo) wings, [nlo,nhi] all, (nhi,whi] wings, rest none
-        const bool n_on = ((cf.pan[0] >> pan) & 1u) && cf.lo[0] <= cf.hi[0];
-        const bool w_on = ((cf.pan[1] >> pan) & 1u) && cf.lo[1] <= cf.hi[1];
-        int nlo = n_on ? cf.lo[0] : STEPS, nhi1 = n_on ? cf.hi[0] + 1 : STEPS;   // [nlo, nhi1)
-        int wlo = w_on ? cf.lo[1] : nlo, whi1 = w_on ? cf.hi[1] + 1 : nhi1;      // [wlo, whi1)
-        wlo = min(wlo, nlo);               // the wing interval is widened to contain the core interval:
-        whi1 = max(whi1, nhi1);            // evaluating a component where it is not needed is harmless
-        if (!n_on) { nlo = whi1; nhi1 = whi1; }
-        // exponentials this evaluation really computes (whole team), for the roofline accounting
-        if (exps) *exps += (unsigned)(G::PW * G::RG) * (unsigned)((nhi1 - nlo) * NB + (whi1 - wlo) * NB);
-        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
-        if (TEAM == 1) {
-            // contiguous steps: the pointers run through the segments
-            StepPtrs sp{rt + g * 2 * K, d + g * NX, w + g * NX, STORE ? model_out + g * NX : nullptr};
-            int i = 0;
-            if (NX < 64) {
-                // 32-pixel stamps have no far field (set_cull is never called for them)
-                row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, STEPS, sp, colA, colB);
-            } else {
-                row_steps<NB, NX, NY, STORE, PREP, 0>(cf, xd, s0, s1, i, wlo, sp, colA, colB);
-                row_steps<NB, NX, NY, STORE, PREP, 1>(cf, xd, s0, s1, i, nlo, sp, colA, colB);
-                row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, nhi1, sp, colA, colB);
-                row_steps<NB, NX, NY, STORE, PREP, 1>(cf, xd, s0, s1, i, whi1, sp, colA, colB);
-                row_steps<NB, NX, NY, STORE, PREP, 0>(cf, xd, s0, s1, i, STEPS, sp, colA, colB);
-            }
-        } else {
-            // a team member owns only STEPS/TEAM steps (no culling in teams): one dense step at a time
+    for (int half = 0; half < Rows<NY>::HALVES; ++half) {
+        build_row_table<NB, TR>(rt, cf, lane, half * TR);
+        const float* dh = d + half * TR * NX;
+        const float* wh = w + half * TR * NX;
+        float* mh = STORE ? model_out + half * TR * NX : nullptr;
 #pragma unroll 1
-            for (int it = tw; it < STEPS; it += TEAM) {
-                const int r0 = it * G::RG + g;
-                StepPtrs sp{rt + r0 * 2 * K, d + r0 * NX, w + r0 * NX, STORE ? model_out + r0 * NX : nullptr};
-                int i = it;
-                row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, it + 1, sp, colA, colB);
+        for (int pan = 0; pan < G::PANELS; ++pan) {
+            const int colA = pan * G::PW + 4 * c + (G::PW / 2) * swap;
+            const int colB = pan * G::PW + 4 * c + (G::PW / 2) * (1 - swap);
+            // segments of this panel (in row steps of this table):
+            //   [0,wlo) none, [wlo,nlo) wings, [nlo,nhi1) all, [nhi1,whi1) wings, [whi1,STEPS) none
+            const bool n_on = ((cf.pan[0] >> pan) & 1u) && cf.lo[0] <= cf.hi[0];
+            const bool w_on = ((cf.pan[1] >> pan) & 1u) && cf.lo[1] <= cf.hi[1];
+            const int base = half * STEPS;
+            int nlo = n_on ? min(max(cf.lo[0] - base, 0), STEPS) : STEPS;
+            int nhi1 = n_on ? min(max(cf.hi[0] + 1 - base, 0), STEPS) : STEPS;
+            if (nlo >= nhi1) { nlo = STEPS; nhi1 = STEPS; }
+            int wlo = w_on ? min(max(cf.lo[1] - base, 0), STEPS) : nlo;
+            int whi1 = w_on ? min(max(cf.hi[1] + 1 - base, 0), STEPS) : nhi1;
+            if (w_on && wlo >= whi1) { wlo = nlo; whi1 = nhi1; }
+            wlo = min(wlo, nlo);               // the wing interval is widened to contain the core interval:
+            whi1 = max(whi1, nhi1);            // evaluating a component where it is not needed is harmless
+            if (nlo >= nhi1) { nlo = whi1; nhi1 = whi1; }
+            if (!cf.fast || TEAM > 1) { wlo = 0; nlo = 0; nhi1 = STEPS; whi1 = STEPS; }   // dense
+            if (exps) *exps += (unsigned)(G::PW * G::RG) * (unsigned)((nhi1 - nlo) * NB + (whi1 - wlo) * NB);
+            float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+            if (cf.fast) {
+                LaneK<NB> lk;
+                lane_consts<NB>(lk, cf, (float)colA + 1.5f, (float)colB + 1.5f);
+                if (TEAM == 1) {
+                    // contiguous steps: the pointers run through the segments
+                    StepPtrs sp{rt + g * T::RS, dh + g * NX, wh + g * NX, STORE ? mh + g * NX : nullptr};
+                    int i = 0;
+                    if (NX < 64) {
+                        // 32-pixel stamps have no far field (set_cull is never called for them)
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, STEPS, sp, colA, colB);
+                    } else {
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 0>(cf, lk, s0, s1, i, wlo, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 1>(cf, lk, s0, s1, i, nlo, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, nhi1, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 1>(cf, lk, s0, s1, i, whi1, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 0>(cf, lk, s0, s1, i, STEPS, sp, colA, colB);
+                    }
+                } else {
+                    // a team member owns only STEPS/TEAM steps (no culling in teams): one dense step at a time
+#pragma unroll 1
+                    for (int it = tw; it < STEPS; it += TEAM) {
+                        const int r0 = it * G::RG + g;
+                        StepPtrs sp{rt + r0 * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr};
+                        int i = it;
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, it + 1, sp, colA, colB);
+                    }
+                }
+            } else {
+                float2 xd[K][4];   // pixel pairs: (0,1) (2,3) of group A, (0,1) (2,3) of group B
+                const float fa = (float)colA, fb = (float)colB;
+                const float2 cols[4] = {make_float2(fa, fa + 1.f), make_float2(fa + 2.f, fa + 3.f),
+                                        make_float2(fb, fb + 1.f), make_float2(fb + 2.f, fb + 3.f)};
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float2 nx0 = make_float2(-cf.x0[k], -cf.x0[k]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xd[k][j] = __fadd2_rn(cols[j], nx0);
+                }
+#pragma unroll 1
+                for (int it = tw; it < STEPS; it += TEAM) {
+                    const int r0 = it * G::RG + g;
+                    StepPtrs sp{rt + r0 * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr};
+                    int i = it;
+                    row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, it + 1, sp, colA, colB);
+                }
             }
+            // FP32 partial sums of one panel (at most 16 steps x 8 pixels over 4 accumulators) -> FP64
+            acc += (double)((s0.x + s0.y) + (s1.x + s1.y));
         }
-        // FP32 partial sums of one panel (at most NY/RG steps x 8 pixels over 4 accumulators) -> FP64
-        acc += (double)((s0.x + s0.y) + (s1.x + s1.y));
     }
     return warp_sum_f64(acc);
 }

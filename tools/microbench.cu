@@ -109,6 +109,56 @@ __global__ void __launch_bounds__(256) pattern2_kernel(float* out, int iters, fl
     if (s.x + s.y == 123.456f) out[0] = s.x;
 }
 
+
+// factorised form (v7): anchors at group centres, per-pixel value = E0 * C_j * R_j; same-shape
+// components share R.  Per row step (8 pixels, 4 components in 2 classes): 8 MUFU + 40 packed ops.
+__global__ void __launch_bounds__(256) pattern3_kernel(float* out, int iters, float a, float b) {
+    float2 dxa[4], C[4][4];
+    float2 sa[2] = {make_float2(-0.15f * a, -0.15f * a), make_float2(-0.02f * a, -0.02f * a)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float v = (float)((threadIdx.x & 7) * 4) + 1.5f - 3.3f * k * b;
+        dxa[k] = make_float2(v, v + 32.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) C[k][j] = make_float2(1.f + 0.01f * j * b + 0.001f * k, 1.f - 0.01f * j * b);
+    }
+    float2 s = make_float2(0.f, 0.f); float fr = (float)(threadIdx.x >> 3);
+    for (int i = 0; i < iters; ++i) {
+        float2 m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = make_float2(6.4f, 6.4f);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float h = 0.001f * b * (fr - 30.f) * (c + 1);
+            const float2 R01 = make_float2(1.f - 3.f * h, 1.f - h), R23 = make_float2(1.f + h, 1.f + 3.f * h);
+            float2 u[4];
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                const int k = 2 * o + c;
+                const float yd = fr - 2.2f * k;
+                const float bb = 0.01f * b * yd, cc = (sa[c].x * yd) * yd;
+                const float2 t = __ffma2_rn(sa[c], dxa[k], make_float2(bb, bb));
+                const float2 q = __ffma2_rn(dxa[k], t, make_float2(cc, cc));
+                const float eA = ex2a(q.x), eB = ex2a(q.y);
+                const float2 ea = make_float2(eA, eA), eb = make_float2(eB, eB);
+                if (o == 0) {
+                    u[0] = __fmul2_rn(C[k][0], ea); u[1] = __fmul2_rn(C[k][1], ea);
+                    u[2] = __fmul2_rn(C[k][2], eb); u[3] = __fmul2_rn(C[k][3], eb);
+                } else {
+                    u[0] = __ffma2_rn(C[k][0], ea, u[0]); u[1] = __ffma2_rn(C[k][1], ea, u[1]);
+                    u[2] = __ffma2_rn(C[k][2], eb, u[2]); u[3] = __ffma2_rn(C[k][3], eb, u[3]);
+                }
+            }
+            m[0] = __ffma2_rn(R01, u[0], m[0]); m[1] = __ffma2_rn(R23, u[1], m[1]);
+            m[2] = __ffma2_rn(R01, u[2], m[2]); m[3] = __ffma2_rn(R23, u[3], m[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 r = __ffma2_rn(make_float2(-0.5f, -0.5f), m[j], make_float2(7.f, 7.f)); s = __ffma2_rn(r, r, s); }
+        fr += 4.f; if (fr > 60.f) fr -= 64.f;
+    }
+    if (s.x + s.y == 123.456f) out[0] = s.x;
+}
+
 template <typename F>
 double time_it(F launch, double ops) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -143,6 +193,7 @@ int main() {
         printf(" 6:%.0f", time_it([&] { mix2_kernel<6><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
         printf(" 8:%.0f", time_it([&] { mix2_kernel<8><<<blocks, 256>>>(d, iters, .999f, .001f); }, ops) / 1e9);
         printf("  pattern2 %.0f", time_it([&] { pattern2_kernel<<<blocks, 256>>>(d, iters, .999f, .001f); }, pops) / 1e9);
+        printf("  pattern3 %.0f (pixel-comp evals, G/s)", time_it([&] { pattern3_kernel<<<blocks, 256>>>(d, iters, .999f, .001f); }, pops) / 1e9);
         printf("  pattern %.0f Gex2/s\n", time_it([&] { pattern_kernel<<<blocks, 256>>>(d, iters, .999f, .001f); }, pops) / 1e9);
     }
     return 0;
