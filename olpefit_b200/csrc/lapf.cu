@@ -110,7 +110,8 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
     const double mine = (lane < P) ? params[b * P + lane] : 0.0;
     stage_trial<NB>(tf[warp], lane, mine, (double)pr.origin[2 * f], (double)pr.origin[2 * f + 1]);
     Coef<NB> cf;
-    load_centres_amps<NB>(cf, tf[warp], pr.floor_index);
+    load_centres_amps<NB>(cf, tf[warp]);
+    cf.floor = tf[warp][pr.floor_index];
     load_shape<NB>(cf, 0, tf[warp]);
     load_shape<NB>(cf, 1, tf[warp]);
     __shared__ __align__(16) float rt[4][Rows<NY>::TR * Tab<NB>::RS];
@@ -232,6 +233,7 @@ struct RunArgs {
     const int32_t* item_first;   // [n_items] offset into walker_of
     const int32_t* item_count;   // [n_items] walkers in the item (<= warps per CTA)
     const int32_t* walker_of;    // local walker indices grouped by frame
+    const int32_t* cta_item;     // [grid + 1] first item of every CTA (batched kernel only)
     double* state;               // [W][P+1]  parameters, chi-square
     const double* shift;         // [W][P+1]  initial state (shift of the running moments)
     double* moments;             // [W][P+1][2] running sum / sum of squares of recorded rows
@@ -310,7 +312,8 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         const double nv = ((a.log_mask >> k) & 1u) ? (pk < 0.0 ? nan("") : pk * step) : pk + step;
 
         stage_trial<NB>(ws.tf, lane, (lane == k) ? nv : p, oxd, oyd);  // :312-313
-        load_centres_amps<NB>(cf, ws.tf, a.floor_index);
+        load_centres_amps<NB>(cf, ws.tf);
+        cf.floor = ws.tf[a.floor_index];
         {
             const float4 s0 = *reinterpret_cast<const float4*>(&ws.shape[0]);
             const float4 s1 = *reinterpret_cast<const float4*>(&ws.shape[4]);
@@ -427,6 +430,162 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
         if (team < a.item_count[it])
             run_walker<NB, NX, NY, TEAM>(a, sd, sw, scratch[warp], rt + warp * (Rows<NY>::TR * Tab<NB>::RS), team_part[team],
                                          team, tw, a.walker_of[a.item_first[it] + team], f, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched form (team_warps = 1, the throughput configuration).  A warp owns up to LW walkers of
+// the staged frame.  Everything that is scalar work per walker -- random numbers, proposal,
+// coefficients of the trial vector, culling bounds, accept/reject, counters, chain row -- is done
+// with ONE WALKER PER LANE, once per round, and costs 1/LW of a warp instruction per update.  In
+// between, the warp evaluates the trial vectors one after the other (a "pass": row table, lane
+// constants, pixel loop, butterfly sum), reading each walker's coefficients from its
+// shared-memory image.  FP64 state lives in global memory (L1/L2 resident: one parameter read
+// and at most one written per update).  The arithmetic per walker is the one of run_walker: chains
+// are bit-identical between the two forms.
+// ---------------------------------------------------------------------------------------------
+template <int NB, int NX, int NY, int LW>
+__device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, const float* sw, float* rt, float* img,
+                                          int wl, int nl, int frame, int lane) {
+    using L = Layout<NB>;
+    using I = CoefImg<NB>;
+    constexpr int P = L::P;
+    const bool mine = wl >= 0;
+    const uint64_t gid = (uint64_t)(a.id_base + (int64_t)wl * a.id_stride);
+    const double oxd = (double)a.origin[2 * frame], oyd = (double)a.origin[2 * frame + 1];
+    double* st = a.state + (size_t)(mine ? wl : 0) * (P + 1);
+    double chi_c = mine ? st[P] : 0.0;
+
+    const int n_upd = (int)a.n_updates;
+    int next_rec = (int)min(a.next_record - a.t0 - 1, (int64_t)0x7fffffff);   // update index that records next
+    int row = 0;
+    unsigned long long n_exps = 0;
+
+#pragma unroll 1
+    for (int u = 0; u < n_upd; ++u) {
+        // ---- one walker per lane: draws, proposal, coefficients of the trial vector -------------
+        int k = 0;
+        double nv = 0.0, lnu = 0.0;
+        if (mine) {
+            const Draw dr = make_draw(a.seed, gid, (uint64_t)(a.t0 + u), P);   // apf_step2.py:302, :64/:68, :143
+            k = dr.k;
+            lnu = dr.lnu;
+            const double wz = a.widths[k] * dr.z;
+            const bool is_log = (a.log_mask >> k) & 1u;
+            double v[P];
+#pragma unroll
+            for (int j = 0; j < P; ++j) v[j] = st[j];
+            double pk = v[0];
+#pragma unroll
+            for (int j = 1; j < P; ++j) pk = (j == k) ? v[j] : pk;
+            // proposal (apf_step2.py:63-70): additive, or multiplicative 10^(w z) for the log10
+            // parameters; log10 of a negative value is nan there, and 0 stays 0.
+            nv = is_log ? (pk < 0.0 ? nan("") : pk * exp10(wz)) : pk + wz;
+#pragma unroll
+            for (int j = 0; j < P; ++j) v[j] = (j == k) ? nv : v[j];            // :312-313
+            double fl = v[2 * NB];
+#pragma unroll
+            for (int j = 2 * NB + 1; j < P; ++j) fl = (j == a.floor_index) ? v[j] : fl;
+            Coef<NB> cf;
+            coef_from_vector<NB>(cf, v, fl, oxd, oyd);
+            set_fast_serial<NB, NX, NY>(cf);
+            if (NX >= 64 && a.cull) set_cull_serial<NB, NX, NY>(cf); else no_cull<NB, NX, NY>(cf);
+            store_coef<NB>(img + lane * I::STRIDE, cf);
+        }
+        __syncwarp();
+
+        // ---- passes: the warp evaluates chi-square of its walkers' trial vectors in turn --------
+        double chi_t = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < nl; ++i) {
+            Coef<NB> cf;
+            load_coef<NB>(cf, img + i * I::STRIDE);
+            unsigned e_upd = 0;
+            const double c = warp_chi2<NB, NX, NY, false, true, 1>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd);   // :314-316
+            if (lane == i) { chi_t = c; n_exps += e_upd; }
+        }
+        __syncwarp();   // every pass has read its image before the next round overwrites it
+
+        // ---- one walker per lane: accept / reject, counters, chain row --------------------------
+        if (mine) {
+            if (a.outside) {
+                double fl = st[a.floor_index];
+                if (k == a.floor_index) fl = nv;
+                chi_t += outside_chi2(a.outside, frame, fl);
+            }
+            // accept iff u < exp(-(chi_t - chi_c)/2) (apf_step2.py:139-148); false on nan
+            const bool acc = lnu < -0.5 * (chi_t - chi_c);
+            atomicAdd(&a.tries[(size_t)wl * P + k], 1u);                  // :304
+            if (acc) {
+                atomicAdd(&a.accepts[(size_t)wl * P + k], 1u);            // :323
+                st[k] = nv;                                               // :325
+                chi_c = chi_t;                                            // :327
+            }
+        }
+        if (u == next_rec) {                                              // :342-351
+            if (mine) {
+#pragma unroll 1
+                for (int j = 0; j <= P; ++j) {
+                    const size_t mi = (size_t)wl * (P + 1) + j;
+                    const double v = (j == P) ? chi_c : st[j];
+                    if (a.chain) a.chain[((size_t)row * a.n_walkers + wl) * (P + 1) + j] = v;
+                    const double dl = v - a.shift[mi];
+                    atomicAdd(&a.moments[2 * mi], dl);                    // single writer: plain RED, in order
+                    atomicAdd(&a.moments[2 * mi + 1], dl * dl);
+                }
+            }
+            ++row;
+            next_rec += a.thin;   // (saturates harmlessly: a launch is shorter than 2^30)
+        }
+    }
+    if (mine) {
+        st[P] = chi_c;
+        a.exps[wl] += n_exps;
+    }
+}
+
+template <int NB, int NX, int NY, int NW, int LW>
+__global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_constant__ RunArgs a) {
+    using I = CoefImg<NB>;
+    constexpr int TAB = Rows<NY>::TR * Tab<NB>::RS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    float* sd = reinterpret_cast<float*>(smem_raw);
+    float* sw = sd + NX * NY;
+    float* rt = sw + NX * NY;                       // [NW][TR][Tab::RS] row tables
+    float* img = rt + NW * TAB;                     // [NW][LW][CoefImg::STRIDE] trial coefficients
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+
+    const int i0 = a.cta_item[blockIdx.x], i1 = a.cta_item[blockIdx.x + 1];
+    int cur_frame = -1;
+    uint32_t phase = 0;
+    for (int it = i0; it < i1; ++it) {
+        const int f = a.item_frame[it];
+        if (f != cur_frame) {
+            __syncthreads();   // every warp has finished reading the previous stamp
+            if (threadIdx.x == 0) {
+                constexpr uint32_t kBytes = NX * NY * sizeof(float);
+                fence_proxy_async();
+                mbar_expect_tx(&bar, 2 * kBytes);
+                tma_bulk_g2s(sd, a.data + (size_t)f * NX * NY, kBytes, &bar);
+                tma_bulk_g2s(sw, a.weight + (size_t)f * NX * NY, kBytes, &bar);
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            cur_frame = f;
+            prep_stamp(sd, sw, NX * NY);            // (d, w) -> (d*sqrt(w), -sqrt(w)), once per staged frame
+            __syncthreads();
+        }
+        // walker j of the item goes to warp j % NW, lane j / NW: the warps' loads differ by at most one
+        const int n = a.item_count[it];
+        const int nl = n > warp ? (n - warp + NW - 1) / NW : 0;
+        const int j = warp + NW * lane;
+        if (nl > 0)
+            run_batch<NB, NX, NY, LW>(a, sd, sw, rt + warp * TAB, img + warp * (LW * I::STRIDE),
+                                      (lane < nl) ? a.walker_of[a.item_first[it] + j] : -1, nl, f, lane);
     }
 }
 
@@ -621,6 +780,9 @@ struct lapf_sampler {
     int32_t* item_frame = nullptr;
     int32_t* item_first = nullptr;
     int32_t* item_count = nullptr;
+    int32_t* cta_item = nullptr;   // batched kernel: first item of every CTA
+    int chunk = 0;                 // batched kernel: walkers per item at most (warps x walkers per warp)
+    int launch_grid = 0;           // batched kernel: CTAs that have work
 };
 
 // Far-field culling (set_cull) is on unless the caller sets bit 0 of lapf_problem.flags or the
@@ -776,9 +938,50 @@ static int launch_gibbs(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
     return LAPF_OK;
 }
 
+template <int NB, int NX, int NW, int LW>
+static int configure_batch(lapf_sampler* s) {
+    auto kern = gibbs_batch_kernel<NB, NX, NX, NW, LW>;
+    s->nw = NW;
+    s->chunk = NW * LW;
+    s->minb = 1;
+    s->smem = sizeof(float) * (2 * NX * NX + NW * Rows<NX>::TR * Tab<NB>::RS + NW * LW * CoefImg<NB>::STRIDE);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    int per_sm = 0, sms = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, s->smem));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    if (per_sm < 1) return fail(LAPF_ERR_CUDA, "batched gibbs kernel does not fit on an SM");
+    s->grid = sms;   // persistent: one CTA per SM
+    return LAPF_OK;
+}
+
+template <int NB, int NX, int NW, int LW>
+static int launch_batch(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
+    gibbs_batch_kernel<NB, NX, NX, NW, LW><<<s->launch_grid, NW * 32, s->smem, st>>>(a);
+    CU(cudaGetLastError());
+    return LAPF_OK;
+}
+
+// walkers per warp (lanes used by the one-walker-per-lane phases): 32, or 16 where the 128-pixel
+// stamp leaves less shared memory for the coefficient images
+#define LAPF_DISPATCH_BATCH(FN, ...)                                                        \
+    do {                                                                                    \
+        const int nb__ = s->cfg.problem.nbody, nx__ = s->cfg.problem.nx;                    \
+        if (nb__ == 2 && nx__ == 32) return FN<2, 32, 16, 32>(__VA_ARGS__);                 \
+        if (nb__ == 2 && nx__ == 64) return FN<2, 64, 16, 32>(__VA_ARGS__);                 \
+        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 12, 16>(__VA_ARGS__);               \
+        if (nb__ == 3 && nx__ == 32) return FN<3, 32, 16, 32>(__VA_ARGS__);                 \
+        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 16, 32>(__VA_ARGS__);                 \
+        if (nb__ == 3 && nx__ == 128) return FN<3, 128, 12, 16>(__VA_ARGS__);               \
+        return fail(LAPF_ERR_INVALID, "unsupported sampler shape nbody=%d nx=%d", nb__, nx__); \
+    } while (0)
+
+static int configure_batch_dispatch(lapf_sampler* s) { LAPF_DISPATCH_BATCH(configure_batch, s); }
+static int launch_batch_dispatch(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
+    LAPF_DISPATCH_BATCH(launch_batch, s, a, st);
+}
+
 #define LAPF_DISPATCH_TEAM(FN, NB_, NX_, NW_, ...)                                          \
     do {                                                                                    \
-        if (s->team == 1) return FN<NB_, NX_, NW_, 1, 1>(__VA_ARGS__);                      \
         if (s->team == 4) return FN<NB_, NX_, NW_, 1, 4>(__VA_ARGS__);                      \
         if (s->team == 16 && NX_ >= 64 && NW_ == 16) return FN<NB_, NX_, 16, 1, (NX_ >= 64 ? 16 : 4)>(__VA_ARGS__); \
     } while (0)
@@ -795,8 +998,12 @@ static int launch_gibbs(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
         return fail(LAPF_ERR_INVALID, "unsupported sampler shape nbody=%d nx=%d team_warps=%d", nb__, nx__, s->team); \
     } while (0)
 
-static int configure_dispatch(lapf_sampler* s) { LAPF_DISPATCH_GIBBS(configure_gibbs, s); }
+static int configure_dispatch(lapf_sampler* s) {
+    if (s->team == 1) return configure_batch_dispatch(s);
+    LAPF_DISPATCH_GIBBS(configure_gibbs, s);
+}
 static int launch_dispatch(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
+    if (s->team == 1) return launch_batch_dispatch(s, a, st);
     LAPF_DISPATCH_GIBBS(launch_gibbs, s, a, st);
 }
 }  // extern "C++"
@@ -805,7 +1012,7 @@ static void free_sampler(lapf_sampler* s) {
     if (!s) return;
     cudaFree(s->state); cudaFree(s->shift); cudaFree(s->moments); cudaFree(s->tries); cudaFree(s->accepts); cudaFree(s->exps);
     cudaFree(s->walker_of); cudaFree(s->frame_start); cudaFree(s->item_frame); cudaFree(s->item_first);
-    cudaFree(s->item_count);
+    cudaFree(s->item_count); cudaFree(s->cta_item);
     delete s;
 }
 
@@ -870,13 +1077,36 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     for (int f = 0; f < F; ++f) start[f + 1] += start[f];
     std::vector<int32_t> order((size_t)W), fill(start.begin(), start.end() - 1);
     for (int64_t w = 0; w < W; ++w) order[fill[fo[w]]++] = (int32_t)w;
-    std::vector<int32_t> it_frame, it_first, it_count;
-    for (int f = 0; f < F; ++f)
-        for (int32_t b = start[f]; b < start[f + 1]; b += s->nw) {
-            it_frame.push_back(f);
-            it_first.push_back(b);
-            it_count.push_back(std::min<int32_t>(s->nw, start[f + 1] - b));
+    std::vector<int32_t> it_frame, it_first, it_count, cta_item;
+    if (s->team == 1) {
+        // batched kernel: CTA b owns the contiguous share [b W / G, (b+1) W / G) of the frame-sorted
+        // walkers, cut into items at frame boundaries and at the CTA's capacity
+        const int64_t G = std::min<int64_t>(s->grid, W);
+        s->launch_grid = (int)G;
+        int f = 0;
+        for (int64_t b = 0; b < G; ++b) {
+            cta_item.push_back((int32_t)it_frame.size());
+            int64_t lo = (W * b) / G;
+            const int64_t hi = (W * (b + 1)) / G;
+            while (lo < hi) {
+                while (start[f + 1] <= lo) ++f;
+                const int64_t n = std::min<int64_t>(std::min<int64_t>(hi, start[f + 1]) - lo, s->chunk);
+                it_frame.push_back(f);
+                it_first.push_back((int32_t)lo);
+                it_count.push_back((int32_t)n);
+                lo += n;
+            }
         }
+        cta_item.push_back((int32_t)it_frame.size());
+    } else {
+        for (int f = 0; f < F; ++f)
+            for (int32_t b = start[f]; b < start[f + 1]; b += s->nw) {
+                it_frame.push_back(f);
+                it_first.push_back(b);
+                it_count.push_back(std::min<int32_t>(s->nw, start[f + 1] - b));
+            }
+        cta_item.push_back(0);
+    }
     s->n_items = (int)it_frame.size();
 
     const size_t nst = (size_t)W * (P + 1);
@@ -891,11 +1121,13 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     CUS(cudaMalloc((void**)&s->item_frame, sizeof(int32_t) * s->n_items));
     CUS(cudaMalloc((void**)&s->item_first, sizeof(int32_t) * s->n_items));
     CUS(cudaMalloc((void**)&s->item_count, sizeof(int32_t) * s->n_items));
+    CUS(cudaMalloc((void**)&s->cta_item, sizeof(int32_t) * cta_item.size()));
     CUS(cudaMemcpyAsync(s->walker_of, order.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, st));
     CUS(cudaMemcpyAsync(s->frame_start, start.data(), sizeof(int32_t) * (F + 1), cudaMemcpyHostToDevice, st));
     CUS(cudaMemcpyAsync(s->item_frame, it_frame.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
     CUS(cudaMemcpyAsync(s->item_first, it_first.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
     CUS(cudaMemcpyAsync(s->item_count, it_count.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
+    CUS(cudaMemcpyAsync(s->cta_item, cta_item.data(), sizeof(int32_t) * cta_item.size(), cudaMemcpyHostToDevice, st));
 
     CUS(cudaStreamSynchronize(st));   // the host vectors above are pageable
     rc = lapf_sampler_reset(s, cfg->init_params, cfg->seed, st);
@@ -1011,7 +1243,7 @@ int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int6
     RunArgs a;
     a.data = pb.data; a.weight = pb.weight; a.origin = pb.origin; a.outside = pb.outside;
     a.item_frame = s->item_frame; a.item_first = s->item_first; a.item_count = s->item_count;
-    a.walker_of = s->walker_of;
+    a.walker_of = s->walker_of; a.cta_item = s->cta_item;
     a.state = s->state; a.shift = s->shift; a.moments = s->moments;
     a.tries = s->tries; a.accepts = s->accepts; a.exps = s->exps;
     a.chain = chain_out;

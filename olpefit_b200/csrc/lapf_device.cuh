@@ -155,7 +155,7 @@ __device__ __forceinline__ void stage_trial(float* tf, int lane, double mine, do
 
 // Centres and amplitudes from the staged vector (build_2d_gaussian, apf_step2.py:95-101).
 template <int NB>
-__device__ __forceinline__ void load_centres_amps(Coef<NB>& cf, const float* tf, int floor_index) {
+__device__ __forceinline__ void load_centres_amps(Coef<NB>& cf, const float* tf) {
     using L = Layout<NB>;
     const float ratio = tf[L::I_RATIO], bkgd = tf[L::I_BKGD];
 #pragma unroll
@@ -169,8 +169,8 @@ __device__ __forceinline__ void load_centres_amps(Coef<NB>& cf, const float* tf,
         cf.amp[2 * o] = a - aw;                           // :97
         cf.amp[2 * o + 1] = aw;
     }
-    cf.floor = tf[floor_index];                           // apf_step2.py:119-120
 }
+// the floor of the model is parameter floor_index of the staged vector (apf_step2.py:119-120)
 
 template <int NB>
 __device__ __forceinline__ void load_shape(Coef<NB>& cf, int which, const float* tf) {
@@ -179,6 +179,85 @@ __device__ __forceinline__ void load_shape(Coef<NB>& cf, int which, const float*
         set_shape<NB>(cf, 1, tf[L::I_SX2], tf[L::I_SY2], tf[L::I_TH2]);
     else
         set_shape<NB>(cf, 0, tf[L::I_SX], tf[L::I_SY], tf[L::I_TH]);
+}
+
+// Shared-memory image of a Coef: 16-byte slots, an ODD number of them per walker, so that both the
+// one-walker-per-lane accesses of the batched sampler and its broadcast reads are conflict-free
+// 128-bit transactions.
+template <int NB>
+struct CoefImg {
+    static constexpr int K = 2 * NB;
+    static constexpr int WORDS = 3 * K + 14;          // x0 y0 amp | sa sb sc floor | lo hi pan fast
+    static constexpr int V4 = ((WORDS + 3) / 4) | 1;
+    static constexpr int STRIDE = 4 * V4;             // floats per walker
+};
+
+template <int NB>
+__device__ __forceinline__ void store_coef(float* __restrict__ dst, const Coef<NB>& cf) {
+    constexpr int K = 2 * NB;
+    using I = CoefImg<NB>;
+    float v[I::STRIDE];
+#pragma unroll
+    for (int i = 0; i < I::STRIDE; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { v[k] = cf.x0[k]; v[K + k] = cf.y0[k]; v[2 * K + k] = cf.amp[k]; }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        v[3 * K + c] = cf.sa[c]; v[3 * K + 2 + c] = cf.sb[c]; v[3 * K + 4 + c] = cf.sc[c];
+        v[3 * K + 7 + c] = __int_as_float(cf.lo[c]); v[3 * K + 9 + c] = __int_as_float(cf.hi[c]);
+        v[3 * K + 11 + c] = __uint_as_float(cf.pan[c]);
+    }
+    v[3 * K + 6] = cf.floor;
+    v[3 * K + 13] = __int_as_float(cf.fast ? 1 : 0);
+#pragma unroll
+    for (int q = 0; q < I::V4; ++q)
+        reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+template <int NB>
+__device__ __forceinline__ void load_coef(Coef<NB>& cf, const float* __restrict__ src) {
+    constexpr int K = 2 * NB;
+    using I = CoefImg<NB>;
+    float v[I::STRIDE];
+#pragma unroll
+    for (int q = 0; q < I::V4; ++q) {
+        const float4 t = reinterpret_cast<const float4*>(src)[q];
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { cf.x0[k] = v[k]; cf.y0[k] = v[K + k]; cf.amp[k] = v[2 * K + k]; }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        cf.sa[c] = v[3 * K + c]; cf.sb[c] = v[3 * K + 2 + c]; cf.sc[c] = v[3 * K + 4 + c];
+        cf.lo[c] = __float_as_int(v[3 * K + 7 + c]); cf.hi[c] = __float_as_int(v[3 * K + 9 + c]);
+        cf.pan[c] = __float_as_uint(v[3 * K + 11 + c]);
+    }
+    cf.floor = v[3 * K + 6];
+    cf.fast = __float_as_int(v[3 * K + 13]) != 0;
+}
+
+// Coefficients of a parameter vector given in FP64 frame coordinates, by ONE thread: the same
+// conversions as stage_trial + load_centres_amps + load_shape, so the numbers are the ones the
+// cooperative path produces.  v[] must be indexed with constants only (registers).
+template <int NB>
+__device__ __forceinline__ void coef_from_vector(Coef<NB>& cf, const double (&v)[Layout<NB>::P], double floor_v,
+                                                 double oxd, double oyd) {
+    using L = Layout<NB>;
+    float tf[L::P + 2 * NB];
+#pragma unroll
+    for (int j = 0; j < L::P; ++j) {
+        if (j < 2 * NB) {
+            const double base = v[j] - ((j & 1) ? oyd : oxd);
+            tf[j] = (float)base;
+            tf[L::P + j] = (float)(base + ((j & 1) ? v[L::I_DY] : v[L::I_DX]));
+        } else {
+            tf[j] = (float)v[j];
+        }
+    }
+    load_centres_amps<NB>(cf, tf);
+    cf.floor = (float)floor_v;
+    set_shape<NB>(cf, 0, tf[L::I_SX], tf[L::I_SY], tf[L::I_TH]);
+    set_shape<NB>(cf, 1, tf[L::I_SX2], tf[L::I_SY2], tf[L::I_TH2]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -287,32 +366,26 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
 // Far-field culling.  |A_k| 2^(q) <= |A_k| 2^(kappa dy^2) for every pixel of a row at distance dy
 // from the component's centre (kappa = sc - sb^2/(4 sa), the exponent maximised over dx), and the
 // same with the roles of x and y swapped for a column panel.  A component whose bound over a whole
-// row step (or panel) is below tau = 2^-25 |floor| -- less than half an ulp of a model value that is
-// at least the floor -- would be rounded away by the FMA that adds it, so those rows skip it: no
-// MUFU, no FFMA, and (for non-negative amplitudes) bit-identical results.  Rows are
+// row step (or panel) is below tau = 2^-27 |floor| is skipped there: the components of a class are
+// added to the pixel as ONE term (see row_steps_fast), and up to four terms below tau sum to less
+// than half an ulp of a model value that is at least the floor, so the FMA that would add them
+// rounds them away: no MUFU, no FFMA, and (for non-negative amplitudes) bit-identical results.  Rows are
 // culled per CLASS (all narrow cores / all wide wings): the active rows of a class are one interval
 // of row steps, so a panel is walked as at most five segments (none, wings, all, wings, none), each
 // a tight loop without per-row tests.  On a 128-pixel stamp the cores matter in ~1/4 of the rows and
 // the wings in ~2/3.  The decision is a pure function of the coefficients (chi-square stays a
 // function of the parameter vector); a nan/inf in them disables culling so it reaches chi-square.
-template <int NB, int NX, int NY>
-__device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
+template <int NX, int NY>
+__device__ __forceinline__ void cull_one(float a, float x0, float y0, float sa, float sb, float sc, float floor_v,
+                                         int& lo, int& hi, uint32_t& pm) {
     using G = Geo<NX>;
-    constexpr int K = 2 * NB;
     constexpr int STEPS = NY / G::RG;
     constexpr uint32_t kAllPans = (1u << G::PANELS) - 1u;
-    // lane k < K works out component k; lanes >= K hold the neutral element
-    float a = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
-#pragma unroll
-    for (int k = 1; k < K; ++k)
-        if (lane == k) { a = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
-    const int sh = lane & 1;
-    const float sa = sh ? cf.sa[1] : cf.sa[0], sb = sh ? cf.sb[1] : cf.sb[0], sc = sh ? cf.sc[1] : cf.sc[0];
     // approximate log2 / divide / sqrt are fine here: the radius gets a whole pixel of slack
-    const float tau = 0x1p-27f * fabsf(cf.floor);
+    const float tau = 0x1p-27f * fabsf(floor_v);
     const float L = __log2f(__fdividef(fabsf(a), tau));    // bits of headroom above tau
-    int lo = 0, hi = STEPS - 1;                            // default: everything (also for nan / inf)
-    uint32_t pm = kAllPans;
+    lo = 0; hi = STEPS - 1;                                // default: everything (also for nan / inf)
+    pm = kAllPans;
     if (L <= 0.f) {                                        // below tau everywhere
         lo = STEPS; hi = -1; pm = 0u;
     } else {
@@ -330,7 +403,24 @@ __device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
                 if (x0 + X >= (float)(p * G::PW) && x0 - X <= (float)(p * G::PW + G::PW - 1)) pm |= 1u << p;
         }
     }
-    if (lane >= K) { lo = STEPS; hi = -1; pm = 0u; }
+}
+
+// cooperative form: lane k < K works out component k, the hulls are formed with shuffles
+template <int NB, int NX, int NY>
+__device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
+    using G = Geo<NX>;
+    constexpr int K = 2 * NB;
+    constexpr int STEPS = NY / G::RG;
+    float a = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k)
+        if (lane == k) { a = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
+    const int sh = lane & 1;
+    const float sa = sh ? cf.sa[1] : cf.sa[0], sb = sh ? cf.sb[1] : cf.sb[0], sc = sh ? cf.sc[1] : cf.sc[0];
+    int lo, hi;
+    uint32_t pm;
+    cull_one<NX, NY>(a, x0, y0, sa, sb, sc, cf.floor, lo, hi, pm);
+    if (lane >= K) { lo = STEPS; hi = -1; pm = 0u; }       // neutral element
     // hull over the components of each class: lanes of equal parity (xor 2, 4 keeps the parity)
 #pragma unroll
     for (int off = 2; off <= 4; off <<= 1) {
@@ -343,6 +433,24 @@ __device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
         cf.lo[c] = __shfl_sync(kFull, lo, c);
         cf.hi[c] = __shfl_sync(kFull, hi, c);
         cf.pan[c] = __shfl_sync(kFull, pm, c);
+    }
+}
+
+// one-thread form (the batched sampler prepares one walker per lane): same decisions
+template <int NB, int NX, int NY>
+__device__ __forceinline__ void set_cull_serial(Coef<NB>& cf) {
+    constexpr int K = 2 * NB;
+    constexpr int STEPS = NY / Geo<NX>::RG;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) { cf.lo[c] = STEPS; cf.hi[c] = -1; cf.pan[c] = 0u; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        int lo, hi;
+        uint32_t pm;
+        cull_one<NX, NY>(cf.amp[k], cf.x0[k], cf.y0[k], cf.sa[k & 1], cf.sb[k & 1], cf.sc[k & 1], cf.floor, lo, hi, pm);
+        cf.lo[k & 1] = min(cf.lo[k & 1], lo);
+        cf.hi[k & 1] = max(cf.hi[k & 1], hi);
+        cf.pan[k & 1] |= pm;
     }
 }
 
@@ -359,6 +467,16 @@ __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
 // that its four pixels are below 2^-46 |A| <= 2^-25 |floor|.  Anything else, nan and inf included,
 // takes the plain loop (one exponential per pixel and component).  The decision is a function of
 // the coefficients only and is the same in every lane.
+template <int NX, int NY>
+__device__ __forceinline__ bool fast_one(float a, float x0, float y0, float yref, float sa, float sb, float sc,
+                                         float floor_v) {
+    const float dxm = fabsf(x0 - 0.5f * NX) + 0.5f * NX;      // >= |anchor - x0| for every anchor column
+    const float argc = 1.5f * (fabsf(sa) * (2.f * dxm + 1.5f) + fabsf(sb * (yref - y0)));
+    const float argr = 1.5f * fabsf(sb) * (fabsf(yref - 0.5f * NY) + 0.5f * NY);
+    return argc <= 40.f && argr <= 40.f && fabsf(sc) <= 1e30f &&
+           fabsf(a) <= 0x1p21f * fabsf(floor_v) && fabsf(a) <= 1e12f;    // all false on nan
+}
+
 template <int NB, int NX, int NY>
 __device__ __forceinline__ void set_fast(Coef<NB>& cf, int lane) {
     constexpr int K = 2 * NB;
@@ -368,13 +486,19 @@ __device__ __forceinline__ void set_fast(Coef<NB>& cf, int lane) {
         if (lane == k) { a = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
     const int sh = lane & 1;
     const float sa = sh ? cf.sa[1] : cf.sa[0], sb = sh ? cf.sb[1] : cf.sb[0], sc = sh ? cf.sc[1] : cf.sc[0];
-    const float yref = sh ? cf.y0[1] : cf.y0[0];
-    const float dxm = fabsf(x0 - 0.5f * NX) + 0.5f * NX;      // >= |anchor - x0| for every anchor column
-    const float argc = 1.5f * (fabsf(sa) * (2.f * dxm + 1.5f) + fabsf(sb * (yref - y0)));
-    const float argr = 1.5f * fabsf(sb) * (fabsf(yref - 0.5f * NY) + 0.5f * NY);
-    const bool ok = argc <= 40.f && argr <= 40.f && fabsf(sc) <= 1e30f &&
-                    fabsf(a) <= 0x1p21f * fabsf(cf.floor) && fabsf(a) <= 1e12f;    // all false on nan
+    const bool ok = fast_one<NX, NY>(a, x0, y0, sh ? cf.y0[1] : cf.y0[0], sa, sb, sc, cf.floor);
     cf.fast = __all_sync(kFull, ok || lane >= K);
+}
+
+template <int NB, int NX, int NY>
+__device__ __forceinline__ void set_fast_serial(Coef<NB>& cf) {
+    constexpr int K = 2 * NB;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        ok = ok && fast_one<NX, NY>(cf.amp[k], cf.x0[k], cf.y0[k], cf.y0[k & 1], cf.sa[k & 1], cf.sb[k & 1],
+                                    cf.sc[k & 1], cf.floor);
+    cf.fast = ok;
 }
 
 // Row steps [i0, i1) of one panel for the component classes KIND says (0: none, the model is the
