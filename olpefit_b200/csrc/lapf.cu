@@ -444,9 +444,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
 // and at most one written per update).  The arithmetic per walker is the one of run_walker: chains
 // are bit-identical between the two forms.
 // ---------------------------------------------------------------------------------------------
-template <int NB, int NX, int NY, int LW>
+template <int NB, int NX, int NY, int LW, bool TM>
 __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, const float* sw, float* rt, float* img,
-                                          int wl, int nl, int frame, int lane) {
+                                          int wl, int nl, int frame, int lane, uint32_t tmem) {
     using L = Layout<NB>;
     using I = CoefImg<NB>;
     constexpr int P = L::P;
@@ -501,7 +501,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
             Coef<NB> cf;
             load_coef<NB>(cf, img + i * I::STRIDE);
             unsigned e_upd = 0;
-            const double c = warp_chi2<NB, NX, NY, false, true, 1>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd);   // :314-316
+            const double c = warp_chi2<NB, NX, NY, false, true, 1, TM>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd, tmem);   // :314-316
             if (lane == i) { chi_t = c; n_exps += e_upd; }
         }
         __syncwarp();   // every pass has read its image before the next round overwrites it
@@ -548,8 +548,13 @@ template <int NB, int NX, int NY, int NW, int LW>
 __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_constant__ RunArgs a) {
     using I = CoefImg<NB>;
     constexpr int TAB = Rows<NY>::TR * Tab<NB>::RS;
+    // stamps of up to 64 x 64 pixels also live in the TMEM pixel store (see tmem_fill_stamp)
+    constexpr bool TM = Geo<NX>::PANELS == 1 && Rows<NY>::HALVES == 1;
+    constexpr uint32_t TM_COLS = TM ? 16 * (NY / Geo<NX>::RG) : 32;
+    static_assert(TM_COLS >= 32 && TM_COLS <= 512 && (TM_COLS & (TM_COLS - 1)) == 0, "TMEM allocations are powers of two");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
     float* sd = reinterpret_cast<float*>(smem_raw);
     float* sw = sd + NX * NY;
     float* rt = sw + NX * NY;                       // [NW][TR][Tab::RS] row tables
@@ -557,7 +562,11 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) mbar_init(&bar, 1);
+    if (TM && warp == 0) tmem_alloc(&tmem_slot, TM_COLS);
+    if (TM) tmem_fence_before_sync();
     __syncthreads();
+    if (TM) tmem_fence_after_sync();
+    const uint32_t tmem_base = TM ? tmem_slot : 0u;
 
     const int i0 = a.cta_item[blockIdx.x], i1 = a.cta_item[blockIdx.x + 1];
     int cur_frame = -1;
@@ -578,14 +587,26 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
             cur_frame = f;
             prep_stamp(sd, sw, NX * NY);            // (d, w) -> (d*sqrt(w), -sqrt(w)), once per staged frame
             __syncthreads();
+            if constexpr (TM) {
+                if (warp < 4) tmem_fill_stamp<NX, NY>(tmem_base, sd, sw, warp, lane);
+                tmem_fence_before_sync();
+                __syncthreads();
+                tmem_fence_after_sync();
+            }
         }
         // walker j of the item goes to warp j % NW, lane j / NW: the warps' loads differ by at most one
         const int n = a.item_count[it];
         const int nl = n > warp ? (n - warp + NW - 1) / NW : 0;
         const int j = warp + NW * lane;
         if (nl > 0)
-            run_batch<NB, NX, NY, LW>(a, sd, sw, rt + warp * TAB, img + warp * (LW * I::STRIDE),
-                                      (lane < nl) ? a.walker_of[a.item_first[it] + j] : -1, nl, f, lane);
+            run_batch<NB, NX, NY, LW, TM>(a, sd, sw, rt + warp * TAB, img + warp * (LW * I::STRIDE),
+                                          (lane < nl) ? a.walker_of[a.item_first[it] + j] : -1, nl, f, lane,
+                                          tmem_base + ((uint32_t)(32 * (warp & 3)) << 16));
+    }
+    if (TM) {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
     }
 }
 

@@ -98,6 +98,48 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// Tensor memory (TMEM) as a per-lane, read-only pixel store.  The sampler never uses the tensor
+// cores, so their 256 KB of TMEM per SM are free: every lane keeps ITS pixels of the staged stamp
+// (prepared data and weight of the 8 columns x NY/RG rows it always works on) in the TMEM lane it
+// is allowed to read -- lane 32 (warp % 4) + lane id, shape .32x32b -- and fetches the 16 values
+// of a row step with one tcgen05.ld instead of four LDS.128.  That takes 2 KB per warp and row
+// step off the shared-memory pipe, which the factorised loop would otherwise saturate.
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {   // one warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t ncols) {          // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                   "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+                   "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+                   "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+// issue the load of 16 consecutive columns; the registers are valid only after tmem_ld16_wait
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t addr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(addr));
+}
+// the operands tie every later use of the registers to the wait
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Coefficients
 // ---------------------------------------------------------------------------------------------
@@ -512,6 +554,7 @@ struct StepPtrs {          // where the next row step of this lane lives
     const float* dp;       // data plane
     const float* wp;       // weight plane
     float* mp;             // model output (STORE only)
+    uint32_t tm;           // TMEM address of the lane's 16 values (TM only)
 };
 
 // model of 8 pixels -> (optional store) -> residuals -> chi-square accumulators
@@ -642,7 +685,7 @@ __device__ __forceinline__ void lane_consts(LaneK<NB>& lk, const Coef<NB>& cf, f
     }
 }
 
-template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND>
+template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND, bool TM = false>
 __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<NB>& lk, float2& s0, float2& s1,
                                                int& i, int i1, StepPtrs& sp, int colA, int colB) {
     using G = Geo<NX>;
@@ -652,12 +695,19 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
     const float* dp = sp.dp;
     const float* wp = sp.wp;
     float* mp = sp.mp;
+    uint32_t tm = sp.tm;
 #pragma unroll 1
     for (; i < i1; ++i) {
-        const float4 dA = *reinterpret_cast<const float4*>(dp + colA);
-        const float4 dB = *reinterpret_cast<const float4*>(dp + colB);
-        const float4 wA = *reinterpret_cast<const float4*>(wp + colA);
-        const float4 wB = *reinterpret_cast<const float4*>(wp + colB);
+        float4 dA, dB, wA, wB;
+        uint32_t tv[16];
+        if (TM) {
+            tmem_ld16_issue(tm, tv);
+        } else {
+            dA = *reinterpret_cast<const float4*>(dp + colA);
+            dB = *reinterpret_cast<const float4*>(dp + colB);
+            wA = *reinterpret_cast<const float4*>(wp + colA);
+            wB = *reinterpret_cast<const float4*>(wp + colB);
+        }
         float2 m[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) m[j] = make_float2(cf.floor, cf.floor);
@@ -693,24 +743,34 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
                 m[2] = __ffma2_rn(R01, u[2], m[2]); m[3] = __ffma2_rn(R23, u[3], m[3]);
             }
         }
+        if (TM) {
+            tmem_ld16_wait(tv);
+            dA = make_float4(__uint_as_float(tv[0]), __uint_as_float(tv[1]), __uint_as_float(tv[2]), __uint_as_float(tv[3]));
+            dB = make_float4(__uint_as_float(tv[4]), __uint_as_float(tv[5]), __uint_as_float(tv[6]), __uint_as_float(tv[7]));
+            wA = make_float4(__uint_as_float(tv[8]), __uint_as_float(tv[9]), __uint_as_float(tv[10]), __uint_as_float(tv[11]));
+            wB = make_float4(__uint_as_float(tv[12]), __uint_as_float(tv[13]), __uint_as_float(tv[14]), __uint_as_float(tv[15]));
+            tm += 16;
+        }
         finish_step<NX, STORE, PREP>(m, dA, dB, wA, wB, mp, colA, colB, s0, s1);
         if (STORE) mp += G::RG * NX;
         rp += G::RG * T::RS;
         dp += G::RG * NX;
         wp += G::RG * NX;
     }
-    sp.rp = rp; sp.dp = dp; sp.wp = wp; sp.mp = mp;
+    sp.rp = rp; sp.dp = dp; sp.wp = wp; sp.mp = mp; sp.tm = tm;
 }
 
 // chi-square of one parameter vector over the stamp by ONE warp (TEAM = 1), or this warp's share
 // of it (TEAM > 1: warp `tw` takes every TEAM-th row step; the caller adds the partials in a fixed
 // order).  Builds the row table(s) in `rt` itself.  `exps` counts the component evaluations
 // (pixels x components) the far-field culling left to do.
-template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1>
+template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1, bool TM = false>
 __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restrict__ rt,
                                             const float* __restrict__ d, const float* __restrict__ w,
                                             float* __restrict__ model_out, int lane, int tw = 0,
-                                            unsigned* exps = nullptr) {
+                                            unsigned* exps = nullptr, uint32_t tmem = 0) {
+    static_assert(!TM || (TEAM == 1 && PREP && Rows<NY>::HALVES == 1 && Geo<NX>::PANELS == 1),
+                  "the TMEM pixel store holds whole prepared stamps of up to 64 x 64 pixels");
     using G = Geo<NX>;
     using T = Tab<NB>;
     constexpr int K = 2 * NB;
@@ -753,24 +813,24 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
                 lane_consts<NB>(lk, cf, (float)colA + 1.5f, (float)colB + 1.5f);
                 if (TEAM == 1) {
                     // contiguous steps: the pointers run through the segments
-                    StepPtrs sp{rt + g * T::RS, dh + g * NX, wh + g * NX, STORE ? mh + g * NX : nullptr};
+                    StepPtrs sp{rt + g * T::RS, dh + g * NX, wh + g * NX, STORE ? mh + g * NX : nullptr, tmem};
                     int i = 0;
                     if (NX < 64) {
                         // 32-pixel stamps have no far field (set_cull is never called for them)
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, STEPS, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 2, TM>(cf, lk, s0, s1, i, STEPS, sp, colA, colB);
                     } else {
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 0>(cf, lk, s0, s1, i, wlo, sp, colA, colB);
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 1>(cf, lk, s0, s1, i, nlo, sp, colA, colB);
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, nhi1, sp, colA, colB);
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 1>(cf, lk, s0, s1, i, whi1, sp, colA, colB);
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 0>(cf, lk, s0, s1, i, STEPS, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 0, TM>(cf, lk, s0, s1, i, wlo, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 1, TM>(cf, lk, s0, s1, i, nlo, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 2, TM>(cf, lk, s0, s1, i, nhi1, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 1, TM>(cf, lk, s0, s1, i, whi1, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 0, TM>(cf, lk, s0, s1, i, STEPS, sp, colA, colB);
                     }
                 } else {
                     // a team member owns only STEPS/TEAM steps (no culling in teams): one dense step at a time
 #pragma unroll 1
                     for (int it = tw; it < STEPS; it += TEAM) {
                         const int r0 = it * G::RG + g;
-                        StepPtrs sp{rt + r0 * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr};
+                        StepPtrs sp{rt + r0 * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr, 0u};
                         int i = it;
                         row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, it + 1, sp, colA, colB);
                     }
@@ -789,7 +849,7 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
 #pragma unroll 1
                 for (int it = tw; it < STEPS; it += TEAM) {
                     const int r0 = it * G::RG + g;
-                    StepPtrs sp{rt + r0 * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr};
+                    StepPtrs sp{rt + r0 * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr, 0u};
                     int i = it;
                     row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, it + 1, sp, colA, colB);
                 }
@@ -799,6 +859,31 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
         }
     }
     return warp_sum_f64(acc);
+}
+
+// Copy of the prepared stamp into the TMEM pixel store: called by warps 0..3 (one per TMEM lane
+// quadrant) after prep_stamp; row step i of the lane goes to columns 16 i .. 16 i + 15 in the order
+// the loop consumes them (data A, data B, weight A, weight B).
+template <int NX, int NY>
+__device__ __forceinline__ void tmem_fill_stamp(uint32_t tmem_base, const float* __restrict__ sd,
+                                                const float* __restrict__ sw, int warp, int lane) {
+    using G = Geo<NX>;
+    static_assert(G::PANELS == 1, "one panel");
+    const int c = lane % G::LPR, g = lane / G::LPR;
+    const int swap = (G::PW == 32) ? (g & 1) : 0;
+    const int colA = 4 * c + (G::PW / 2) * swap, colB = 4 * c + (G::PW / 2) * (1 - swap);
+    const uint32_t addr = tmem_base + ((uint32_t)(32 * warp) << 16);
+#pragma unroll 1
+    for (int i = 0; i < NY / G::RG; ++i) {
+        const int r = i * G::RG + g;
+        const float4 dA = *reinterpret_cast<const float4*>(sd + r * NX + colA);
+        const float4 dB = *reinterpret_cast<const float4*>(sd + r * NX + colB);
+        const float4 wA = *reinterpret_cast<const float4*>(sw + r * NX + colA);
+        const float4 wB = *reinterpret_cast<const float4*>(sw + r * NX + colB);
+        const float v[16] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w, wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+        tmem_st16(addr + 16 * i, v);
+    }
+    tmem_wait_st();
 }
 
 // In-place conversion of a staged stamp to (d*sqrt(w), -sqrt(w)); called by the whole CTA.
