@@ -114,7 +114,7 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
     cf.floor = tf[warp][pr.floor_index];
     load_shape<NB>(cf, 0, tf[warp]);
     load_shape<NB>(cf, 1, tf[warp]);
-    __shared__ __align__(16) float rt[4][Rows<NY>::TR * Tab<NB>::RS];
+    __shared__ __align__(16) float rt[4][Scratch<NB, NY>::FLOATS];
     set_fast<NB, NX, NY>(cf, lane);
     if (NX >= 64 && pr.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
     const size_t off = (size_t)f * NX * NY;
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
     __shared__ uint64_t bar;
     float* sd = reinterpret_cast<float*>(smem_raw);
     float* sw = sd + NX * NY;
-    float* rt = sw + NX * NY;                       // [NW][TR][Tab::RS] row tables
+    float* rt = sw + NX * NY;                       // [NW] row + column tables (Scratch)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
         }
         const int team = warp / TEAM, tw = warp % TEAM;
         if (team < a.item_count[it])
-            run_walker<NB, NX, NY, TEAM>(a, sd, sw, scratch[warp], rt + warp * (Rows<NY>::TR * Tab<NB>::RS), team_part[team],
+            run_walker<NB, NX, NY, TEAM>(a, sd, sw, scratch[warp], rt + warp * Scratch<NB, NY, TEAM>::FLOATS, team_part[team],
                                          team, tw, a.walker_of[a.item_first[it] + team], f, lane);
     }
 }
@@ -547,9 +547,9 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
 template <int NB, int NX, int NY, int NW, int LW>
 __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_constant__ RunArgs a) {
     using I = CoefImg<NB>;
-    constexpr int TAB = Rows<NY>::TR * Tab<NB>::RS;
+    constexpr int TAB = Scratch<NB, NY>::FLOATS;
     // stamps of up to 64 x 64 pixels also live in the TMEM pixel store (see tmem_fill_stamp)
-    constexpr bool TM = Geo<NX>::PANELS == 1 && Rows<NY>::HALVES == 1;
+    constexpr bool TM = Geo<NX>::PANELS == 1 && Rows<NY, 1>::HALVES == 1;
     constexpr uint32_t TM_COLS = TM ? 16 * (NY / Geo<NX>::RG) : 32;
     static_assert(TM_COLS >= 32 && TM_COLS <= 512 && (TM_COLS & (TM_COLS - 1)) == 0, "TMEM allocations are powers of two");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
     __shared__ uint32_t tmem_slot;
     float* sd = reinterpret_cast<float*>(smem_raw);
     float* sw = sd + NX * NY;
-    float* rt = sw + NX * NY;                       // [NW][TR][Tab::RS] row tables
+    float* rt = sw + NX * NY;                       // [NW] row + column tables (Scratch)
     float* img = rt + NW * TAB;                     // [NW][LW][CoefImg::STRIDE] trial coefficients
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -941,7 +941,7 @@ static int configure_gibbs(lapf_sampler* s) {
     auto kern = gibbs_kernel<NB, NX, NX, NW, MINB, TEAM>;
     s->nw = NW / TEAM;   // walkers per CTA item
     s->minb = MINB;
-    s->smem = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * Rows<NX>::TR * Tab<NB>::RS;
+    s->smem = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * Scratch<NB, NX, TEAM>::FLOATS;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, s->smem));
@@ -965,7 +965,7 @@ static int configure_batch(lapf_sampler* s) {
     s->nw = NW;
     s->chunk = NW * LW;
     s->minb = 1;
-    s->smem = sizeof(float) * (2 * NX * NX + NW * Rows<NX>::TR * Tab<NB>::RS + NW * LW * CoefImg<NB>::STRIDE);
+    s->smem = sizeof(float) * (2 * NX * NX + NW * Scratch<NB, NX>::FLOATS + NW * LW * CoefImg<NB>::STRIDE);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, s->smem));
@@ -982,16 +982,16 @@ static int launch_batch(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
     return LAPF_OK;
 }
 
-// walkers per warp (lanes used by the one-walker-per-lane phases): 32, or 16 where the 128-pixel
-// stamp leaves less shared memory for the coefficient images
+// walkers per warp (lanes used by the one-walker-per-lane phases): 32, fewer where the stamp or
+// the 3-body tables leave less shared memory for the coefficient images
 #define LAPF_DISPATCH_BATCH(FN, ...)                                                        \
     do {                                                                                    \
         const int nb__ = s->cfg.problem.nbody, nx__ = s->cfg.problem.nx;                    \
         if (nb__ == 2 && nx__ == 32) return FN<2, 32, 16, 32>(__VA_ARGS__);                 \
         if (nb__ == 2 && nx__ == 64) return FN<2, 64, 16, 32>(__VA_ARGS__);                 \
-        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 12, 16>(__VA_ARGS__);               \
+        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 16, 16>(__VA_ARGS__);               \
         if (nb__ == 3 && nx__ == 32) return FN<3, 32, 16, 32>(__VA_ARGS__);                 \
-        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 16, 32>(__VA_ARGS__);                 \
+        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 16, 24>(__VA_ARGS__);                 \
         if (nb__ == 3 && nx__ == 128) return FN<3, 128, 12, 16>(__VA_ARGS__);               \
         return fail(LAPF_ERR_INVALID, "unsupported sampler shape nbody=%d nx=%d", nb__, nx__); \
     } while (0)

@@ -325,39 +325,58 @@ struct Geo {
 };
 
 // Row table: everything that depends on the row only, computed ONCE per proposal by the warp
-// (row r by lane r mod 32) instead of once per row step by every lane.  One entry of Tab::RS floats
-// per row:
-//   [2k], [2k+1]         sb_k * dy_k,  sc_k * dy_k^2     (dy_k = r - y0_k), for component k < K
-//   [2K + 4c .. +3]      2^(j h) for j = -3, -1, 1, 3,  h = sb_c * (r - y0_c) / 2, for shape class c
+// (one or two rows per lane) instead of once per row step by every lane.  One entry of Tab::RS
+// floats per row r:
+//   [2k], [2k+1]          sb_k * dy_k,  sc_k * dy_k^2     (dy_k = r - y0_k), for component k < K
+//   [2K + 4c .. +3]       2^(j h)  for j = -3, -1, 1, 3,  h  = sb_c (r - y0_c) / 2,   shape class c
+//   [2K + 8 + 4c .. +3]   2^(j h') for j = -3, -1, 1, 3,  h' = h + sa_c * D
 // The first pair gives the exponent of component k at any column of the row:
 //   q = fma(dx, fma(sa, dx, sb*dy), sc*dy^2);
-// the second the factor that moves it half a pixel / one and a half pixels left or right of an
-// anchor column (see row_steps_fast).  y0_c is the centre of the class's FIRST component; the
-// other components of the class fold their offset into the lane constants.
-// A table covers TR = min(NY, 64) rows; 128-pixel stamps are walked as two halves.  The entry is
-// padded to 20 floats so the 4 (or 8) row groups of a warp read distinct banks.
+// the second the factors that move it half a pixel / one and a half pixels left or right of the
+// anchor column of a lane's column group A, the third the same for its group B, whose anchor is
+// D = +-PW/2 columns away (see row_steps_fast; the sign follows the row for 32-pixel panels, where
+// odd rows take their groups in swapped order).  y0_c is the centre of the class's FIRST component;
+// the other components of the class fold their offset into the lane constants.
+// The entry is padded to 28 floats so the 4 (or 8) row groups of a warp read distinct banks.
 template <int NB>
 struct Tab {
     static constexpr int K = 2 * NB;
-    static constexpr int RS = 20;
-    static constexpr int OFF_R = 2 * K;
-    static_assert(OFF_R + 8 <= RS, "row table entry too small");
+    static constexpr int RS = 28;
+    static constexpr int OFF_RA = 2 * K;
+    static constexpr int OFF_RB = 2 * K + 8;
+    static_assert(OFF_RB + 8 <= RS && OFF_RA % 4 == 0, "row table entry layout");
 };
 
-template <int NY>
+// A table covers TR rows of the stamp; taller stamps are walked table by table ("half").  A team
+// member (TEAM warps share one walker, warp tw takes every TEAM-th row step) only builds the
+// TR / TEAM rows it evaluates.
+template <int NY, int TEAM = 1>
 struct Rows {
-    static constexpr int TR = NY < 64 ? NY : 64;   // rows per table
+    static constexpr int TR = (NY >= 128 && TEAM == 1) ? 32 : (NY < 64 ? NY : 64);   // rows per table
     static constexpr int HALVES = NY / TR;
-    static_assert(NY % TR == 0 && TR % 32 == 0, "unsupported stamp height");
+    static constexpr int NR = TR / TEAM;                                             // rows a warp builds
+    static_assert(NY % TR == 0 && TR % TEAM == 0, "unsupported stamp height");
 };
 
-template <int NB, int TR>
-__device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Coef<NB>& cf, int lane, int row0) {
+// per-warp shared-memory scratch of the pixel loop: the row table, then the column table
+// (coop_consts: [component][group-A anchor 0..7][4 pixel offsets])
+template <int NB, int NY, int TEAM = 1>
+struct Scratch {
+    static constexpr int TAB = Rows<NY, TEAM>::NR * Tab<NB>::RS;
+    static constexpr int CT = 2 * NB * 8 * 4;
+    static constexpr int FLOATS = TAB + CT;
+};
+
+template <int NB, int NX, int TR, int TEAM>
+__device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Coef<NB>& cf, int lane, int row0, int tw) {
     constexpr int K = 2 * NB;
+    constexpr int NR = TR / TEAM;
+    constexpr int RG = Geo<NX>::RG;
+    constexpr float HALF = 0.5f * Geo<NX>::PW;
     using T = Tab<NB>;
     __syncwarp();   // readers of the previous table are done
-    if (TR == 64) {
-        // two rows (r, r+32) per pass, as the two halves of packed FP32 operations
+    if (NR == 64) {
+        // two rows (r, r+32) per pass, as the two halves of packed FP32 operations (TEAM = 1 here)
         const float2 fr = make_float2((float)(row0 + lane), (float)(row0 + 32 + lane));
         float4* o0 = reinterpret_cast<float4*>(rt + lane * T::RS);
         float4* o1 = reinterpret_cast<float4*>(rt + (32 + lane) * T::RS);
@@ -374,31 +393,45 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
             o0[q] = make_float4(v[4 * q].x, v[4 * q + 1].x, v[4 * q + 2].x, v[4 * q + 3].x);
             o1[q] = make_float4(v[4 * q].y, v[4 * q + 1].y, v[4 * q + 2].y, v[4 * q + 3].y);
         }
+        // 64-row tables belong to 64-pixel panels: group B is always +PW/2 away (no swapped rows)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const float2 h = __fmul2_rn(v[2 * c], make_float2(0.5f, 0.5f));     // sb_c * dy_c / 2
             const float2 h3 = __fmul2_rn(v[2 * c], make_float2(1.5f, 1.5f));
-            o0[T::OFF_R / 4 + c] = make_float4(ex2_approx(-h3.x), ex2_approx(-h.x), ex2_approx(h.x), ex2_approx(h3.x));
-            o1[T::OFF_R / 4 + c] = make_float4(ex2_approx(-h3.y), ex2_approx(-h.y), ex2_approx(h.y), ex2_approx(h3.y));
+            o0[T::OFF_RA / 4 + c] = make_float4(ex2_approx(-h3.x), ex2_approx(-h.x), ex2_approx(h.x), ex2_approx(h3.x));
+            o1[T::OFF_RA / 4 + c] = make_float4(ex2_approx(-h3.y), ex2_approx(-h.y), ex2_approx(h.y), ex2_approx(h3.y));
+            const float sd = cf.sa[c] * HALF;
+            const float2 g = __fadd2_rn(h, make_float2(sd, sd));
+            const float2 g3 = __fmul2_rn(g, make_float2(3.f, 3.f));
+            o0[T::OFF_RB / 4 + c] = make_float4(ex2_approx(-g3.x), ex2_approx(-g.x), ex2_approx(g.x), ex2_approx(g3.x));
+            o1[T::OFF_RB / 4 + c] = make_float4(ex2_approx(-g3.y), ex2_approx(-g.y), ex2_approx(g.y), ex2_approx(g3.y));
         }
     } else {
 #pragma unroll
-        for (int r0 = 0; r0 < TR; r0 += 32) {
-            const float fr = (float)(row0 + r0 + lane);
-            float4* o = reinterpret_cast<float4*>(rt + (r0 + lane) * T::RS);
-            float v[2 * K];
+        for (int j0 = 0; j0 < NR; j0 += 32) {
+            const int j = j0 + lane;                    // local row: row step j / RG of this warp, row group j % RG
+            if (NR % 32 == 0 || j < NR) {
+                const int r = row0 + ((j / RG) * TEAM + tw) * RG + (j % RG);
+                const float fr = (float)r;
+                float4* o = reinterpret_cast<float4*>(rt + j * T::RS);
+                float v[2 * K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const float yd = fr - cf.y0[k];
-                v[2 * k] = cf.sb[k & 1] * yd;
-                v[2 * k + 1] = (cf.sc[k & 1] * yd) * yd;
-            }
+                for (int k = 0; k < K; ++k) {
+                    const float yd = fr - cf.y0[k];
+                    v[2 * k] = cf.sb[k & 1] * yd;
+                    v[2 * k + 1] = (cf.sc[k & 1] * yd) * yd;
+                }
 #pragma unroll
-            for (int q = 0; q < 2 * K / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int q = 0; q < 2 * K / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                // odd rows of a 32-pixel panel take their column groups in swapped order
+                const float dlt = (Geo<NX>::PW == 32 && (r & 1)) ? -HALF : HALF;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const float h = v[2 * c] * 0.5f, h3 = v[2 * c] * 1.5f;
-                o[T::OFF_R / 4 + c] = make_float4(ex2_approx(-h3), ex2_approx(-h), ex2_approx(h), ex2_approx(h3));
+                for (int c = 0; c < 2; ++c) {
+                    const float h = v[2 * c] * 0.5f, h3 = v[2 * c] * 1.5f;
+                    o[T::OFF_RA / 4 + c] = make_float4(ex2_approx(-h3), ex2_approx(-h), ex2_approx(h), ex2_approx(h3));
+                    const float g = h + cf.sa[c] * dlt, g3 = g * 3.f;
+                    o[T::OFF_RB / 4 + c] = make_float4(ex2_approx(-g3), ex2_approx(-g), ex2_approx(g), ex2_approx(g3));
+                }
             }
         }
     }
@@ -504,7 +537,7 @@ __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
 
 // The factorised pixel loop multiplies factors whose exponents can be large although their sum is
 // not.  It is used only when, for every pixel of the stamp, the column factor's exponent
-// |j (sa (2 dxa + j) + w_k)| and the row factor's |1.5 sb dy| stay below 40 -- no factor overflows
+// |j (sa (2 dxa + j) + w_k)| and the row factor's |1.5 (sb dy + sa PW)| stay below 40 -- no factor overflows
 // or underflows on its own -- and when an anchor exponential that underflows (q0 < -126) implies
 // that its four pixels are below 2^-46 |A| <= 2^-25 |floor|.  Anything else, nan and inf included,
 // takes the plain loop (one exponential per pixel and component).  The decision is a function of
@@ -514,7 +547,7 @@ __device__ __forceinline__ bool fast_one(float a, float x0, float y0, float yref
                                          float floor_v) {
     const float dxm = fabsf(x0 - 0.5f * NX) + 0.5f * NX;      // >= |anchor - x0| for every anchor column
     const float argc = 1.5f * (fabsf(sa) * (2.f * dxm + 1.5f) + fabsf(sb * (yref - y0)));
-    const float argr = 1.5f * fabsf(sb) * (fabsf(yref - 0.5f * NY) + 0.5f * NY);
+    const float argr = 1.5f * (fabsf(sb) * (fabsf(yref - 0.5f * NY) + 0.5f * NY) + fabsf(sa) * Geo<NX>::PW);
     return argc <= 40.f && argr <= 40.f && fabsf(sc) <= 1e30f &&
            fabsf(a) <= 0x1p21f * fabsf(floor_v) && fabsf(a) <= 1e12f;    // all false on nan
 }
@@ -651,37 +684,59 @@ __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)
 //     C_kj    = A_k 2^(j (sa (2 dxa_k + j) + sb (y0_c - y0_k)))    lane constant (registers)
 //     R_cj(r) = 2^(j sb (r - y0_c))                  row table, shared by the class
 // and a class adds  R_cj * sum_k C_kj E_k  to the pixel: per pixel pair NB + 1 packed operations
-// for NB components, plus 2 FFMA2 + 2 MUFU per component for the two anchors.  A row step of
-// 8 pixels x 4 components is 40 packed FP32 instructions and 8 MUFU (plain loop: 56 and 32):
-// the loop is bound by the FP32 pipe, not the SFU.
+// for NB components, plus 2 FFMA2 + 2 MUFU per component for the two anchors.  The anchor of
+// group B is D = +-PW/2 columns from group A's, so C_kj(B) = C_kj(A) 2^(2 j sa D): the lane keeps
+// the constants of group A only and group B takes its factor from a second row-table entry
+// R'_cj = R_cj 2^(2 j sa D).  A row step of 8 pixels x 4 components is 40 packed FP32
+// instructions and 8 MUFU (plain loop: 56 and 32): the loop is bound by the FP32 pipe, not the SFU.
 template <int NB>
 struct LaneK {
     static constexpr int K = 2 * NB;
     float2 dxa[K];       // (group A, group B) anchor offset to the centre of component k
-    float2 C[K][4];      // pixel pairs A(-1.5,-0.5) A(0.5,1.5) B(-1.5,-0.5) B(0.5,1.5)
+    float2 C[K][2];      // group A, pixel pairs (-1.5,-0.5) and (0.5,1.5)
 };
 
-template <int NB>
-__device__ __forceinline__ void lane_consts(LaneK<NB>& lk, const Coef<NB>& cf, float xaA, float xaB) {
+// The C_kj of the 8 group-A anchors of a panel (columns 4a + 1.5, a = 0..7), worked out once per
+// proposal by the warp -- lane (a, k) does component k at anchor a -- and handed round through the
+// column table ct[k][a][4]; every lane then reads the 4K values of its own anchor.
+template <int NB, int NX>
+__device__ __forceinline__ void coop_consts(LaneK<NB>& lk, float* __restrict__ ct, const Coef<NB>& cf, int lane,
+                                            int pan, int colA, int colB) {
+    using G = Geo<NX>;
     constexpr int K = 2 * NB;
-    const float2 jlo = make_float2(-1.5f, -0.5f), jhi = make_float2(0.5f, 1.5f);
+    __syncwarp();   // readers of the previous column table are done
+    const int a = lane & 7;
+    const float xa = (float)(pan * G::PW + 4 * a) + 1.5f;
+#pragma unroll
+    for (int kk0 = 0; kk0 < K; kk0 += 4) {
+        const int kk = kk0 + (lane >> 3);
+        if (K % 4 == 0 || kk < K) {
+            float amp = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k)
+                if (kk == k) { amp = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
+            const int c = kk & 1;
+            const float sa = c ? cf.sa[1] : cf.sa[0], sb = c ? cf.sb[1] : cf.sb[0];
+            const float wk = sb * ((c ? cf.y0[1] : cf.y0[0]) - y0);      // exactly 0 for the class's first component
+            const float d2 = 2.f * (xa - x0);
+            const float2 w2 = make_float2(wk, wk), sa2 = make_float2(sa, sa), am = make_float2(amp, amp);
+            const float2 jlo = make_float2(-1.5f, -0.5f), jhi = make_float2(0.5f, 1.5f);
+            const float2 alo = __fmul2_rn(jlo, __ffma2_rn(sa2, __fadd2_rn(make_float2(d2, d2), jlo), w2));
+            const float2 ahi = __fmul2_rn(jhi, __ffma2_rn(sa2, __fadd2_rn(make_float2(d2, d2), jhi), w2));
+            const float2 clo = __fmul2_rn(am, make_float2(ex2_approx(alo.x), ex2_approx(alo.y)));
+            const float2 chi = __fmul2_rn(am, make_float2(ex2_approx(ahi.x), ex2_approx(ahi.y)));
+            reinterpret_cast<float4*>(ct)[kk * 8 + a] = make_float4(clo.x, clo.y, chi.x, chi.y);
+        }
+    }
+    __syncwarp();
+    const int mine = ((colA - pan * G::PW) >> 2) & 7;   // this lane's group-A anchor
+    const float xaA = (float)colA + 1.5f, xaB = (float)colB + 1.5f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const int c = k & 1;
-        const float wk = (k < 2) ? 0.f : cf.sb[c] * (cf.y0[c] - cf.y0[k]);
-        const float2 w2 = make_float2(wk, wk), sa2 = make_float2(cf.sa[c], cf.sa[c]);
-        const float2 am = make_float2(cf.amp[k], cf.amp[k]);
+        const float4 v = reinterpret_cast<const float4*>(ct)[k * 8 + mine];
+        lk.C[k][0] = make_float2(v.x, v.y);
+        lk.C[k][1] = make_float2(v.z, v.w);
         lk.dxa[k] = make_float2(xaA - cf.x0[k], xaB - cf.x0[k]);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const float d2 = 2.f * (g ? lk.dxa[k].y : lk.dxa[k].x);
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                const float2 jj = p ? jhi : jlo;
-                const float2 arg = __fmul2_rn(jj, __ffma2_rn(sa2, __fadd2_rn(make_float2(d2, d2), jj), w2));
-                lk.C[k][2 * g + p] = __fmul2_rn(am, make_float2(ex2_approx(arg.x), ex2_approx(arg.y)));
-            }
-        }
     }
 }
 
@@ -720,8 +775,8 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
             }
 #pragma unroll
             for (int c = (KIND == 2 ? 0 : 1); c < 2; ++c) {
-                const float4 R = reinterpret_cast<const float4*>(rp + T::OFF_R)[c];
-                const float2 R01 = make_float2(R.x, R.y), R23 = make_float2(R.z, R.w);
+                const float4 RA = reinterpret_cast<const float4*>(rp + T::OFF_RA)[c];
+                const float4 RB = reinterpret_cast<const float4*>(rp + T::OFF_RB)[c];
                 const float2 sa2 = make_float2(cf.sa[c], cf.sa[c]);
                 float2 u[4];
 #pragma unroll
@@ -733,14 +788,14 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
                     const float2 ea = make_float2(eA, eA), eb = make_float2(eB, eB);
                     if (o == 0) {
                         u[0] = __fmul2_rn(lk.C[k][0], ea); u[1] = __fmul2_rn(lk.C[k][1], ea);
-                        u[2] = __fmul2_rn(lk.C[k][2], eb); u[3] = __fmul2_rn(lk.C[k][3], eb);
+                        u[2] = __fmul2_rn(lk.C[k][0], eb); u[3] = __fmul2_rn(lk.C[k][1], eb);
                     } else {
                         u[0] = __ffma2_rn(lk.C[k][0], ea, u[0]); u[1] = __ffma2_rn(lk.C[k][1], ea, u[1]);
-                        u[2] = __ffma2_rn(lk.C[k][2], eb, u[2]); u[3] = __ffma2_rn(lk.C[k][3], eb, u[3]);
+                        u[2] = __ffma2_rn(lk.C[k][0], eb, u[2]); u[3] = __ffma2_rn(lk.C[k][1], eb, u[3]);
                     }
                 }
-                m[0] = __ffma2_rn(R01, u[0], m[0]); m[1] = __ffma2_rn(R23, u[1], m[1]);
-                m[2] = __ffma2_rn(R01, u[2], m[2]); m[3] = __ffma2_rn(R23, u[3], m[3]);
+                m[0] = __ffma2_rn(make_float2(RA.x, RA.y), u[0], m[0]); m[1] = __ffma2_rn(make_float2(RA.z, RA.w), u[1], m[1]);
+                m[2] = __ffma2_rn(make_float2(RB.x, RB.y), u[2], m[2]); m[3] = __ffma2_rn(make_float2(RB.z, RB.w), u[3], m[3]);
             }
         }
         if (TM) {
@@ -762,28 +817,32 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
 
 // chi-square of one parameter vector over the stamp by ONE warp (TEAM = 1), or this warp's share
 // of it (TEAM > 1: warp `tw` takes every TEAM-th row step; the caller adds the partials in a fixed
-// order).  Builds the row table(s) in `rt` itself.  `exps` counts the component evaluations
-// (pixels x components) the far-field culling left to do.
+// order).  Builds the row and column tables in `scratch` (Scratch<NB, NY, TEAM>::FLOATS floats of
+// this warp's own shared memory) itself.  `exps` counts the component evaluations (pixels x
+// components) the far-field culling left to do.
 template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1, bool TM = false>
-__device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restrict__ rt,
+__device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restrict__ scratch,
                                             const float* __restrict__ d, const float* __restrict__ w,
                                             float* __restrict__ model_out, int lane, int tw = 0,
                                             unsigned* exps = nullptr, uint32_t tmem = 0) {
-    static_assert(!TM || (TEAM == 1 && PREP && Rows<NY>::HALVES == 1 && Geo<NX>::PANELS == 1),
-                  "the TMEM pixel store holds whole prepared stamps of up to 64 x 64 pixels");
     using G = Geo<NX>;
     using T = Tab<NB>;
+    using R = Rows<NY, TEAM>;
     constexpr int K = 2 * NB;
-    constexpr int TR = Rows<NY>::TR;
+    constexpr int TR = R::TR;
     constexpr int STEPS = TR / G::RG;            // row steps per table (per panel)
+    static_assert(!TM || (TEAM == 1 && PREP && R::HALVES == 1 && G::PANELS == 1),
+                  "the TMEM pixel store holds whole prepared stamps of up to 64 x 64 pixels");
     static_assert(TR % G::RG == 0, "unsupported stamp height");
     static_assert(STEPS % TEAM == 0, "team size must divide the row steps");
+    float* rt = scratch;
+    float* ct = scratch + Scratch<NB, NY, TEAM>::TAB;
     const int c = lane % G::LPR, g = lane / G::LPR;
     const int swap = (G::PW == 32) ? (g & 1) : 0;
     double acc = 0.0;
 #pragma unroll 1
-    for (int half = 0; half < Rows<NY>::HALVES; ++half) {
-        build_row_table<NB, TR>(rt, cf, lane, half * TR);
+    for (int half = 0; half < R::HALVES; ++half) {
+        build_row_table<NB, NX, TR, TEAM>(rt, cf, lane, half * TR, tw);
         const float* dh = d + half * TR * NX;
         const float* wh = w + half * TR * NX;
         float* mh = STORE ? model_out + half * TR * NX : nullptr;
@@ -810,7 +869,7 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
             float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
             if (cf.fast) {
                 LaneK<NB> lk;
-                lane_consts<NB>(lk, cf, (float)colA + 1.5f, (float)colB + 1.5f);
+                coop_consts<NB, NX>(lk, ct, cf, lane, pan, colA, colB);
                 if (TEAM == 1) {
                     // contiguous steps: the pointers run through the segments
                     StepPtrs sp{rt + g * T::RS, dh + g * NX, wh + g * NX, STORE ? mh + g * NX : nullptr, tmem};
@@ -826,13 +885,14 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
                         row_steps_fast<NB, NX, NY, STORE, PREP, 0, TM>(cf, lk, s0, s1, i, STEPS, sp, colA, colB);
                     }
                 } else {
-                    // a team member owns only STEPS/TEAM steps (no culling in teams): one dense step at a time
+                    // a team member owns only STEPS/TEAM steps (no culling in teams): one dense step at a time;
+                    // its table holds just those rows
 #pragma unroll 1
-                    for (int it = tw; it < STEPS; it += TEAM) {
-                        const int r0 = it * G::RG + g;
-                        StepPtrs sp{rt + r0 * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr, 0u};
-                        int i = it;
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, it + 1, sp, colA, colB);
+                    for (int mth = 0; mth < STEPS / TEAM; ++mth) {
+                        const int r0 = (mth * TEAM + tw) * G::RG + g;
+                        StepPtrs sp{rt + (mth * G::RG + g) * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr, 0u};
+                        int i = 0;
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, 1, sp, colA, colB);
                     }
                 }
             } else {
@@ -847,11 +907,11 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
                     for (int j = 0; j < 4; ++j) xd[k][j] = __fadd2_rn(cols[j], nx0);
                 }
 #pragma unroll 1
-                for (int it = tw; it < STEPS; it += TEAM) {
-                    const int r0 = it * G::RG + g;
-                    StepPtrs sp{rt + r0 * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr, 0u};
-                    int i = it;
-                    row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, it + 1, sp, colA, colB);
+                for (int mth = 0; mth < STEPS / TEAM; ++mth) {
+                    const int r0 = (mth * TEAM + tw) * G::RG + g;
+                    StepPtrs sp{rt + (mth * G::RG + g) * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr, 0u};
+                    int i = 0;
+                    row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, 1, sp, colA, colB);
                 }
             }
             // FP32 partial sums of one panel (at most 16 steps x 8 pixels over 4 accumulators) -> FP64
