@@ -338,7 +338,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         }
         set_fast<NB, NX, NY>(cf, lane);
         // in a team the update time is set by the warp with the busiest rows: culling cannot help there
-        if (NX >= 64 && TEAM == 1 && a.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
+        if (NX >= 64 && TEAM == 1 && a.cull) set_cull<NB, NX, NY, TEAM>(cf, lane); else no_cull<NB, NX, NY, TEAM>(cf);
         unsigned e_upd = 0;
         double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw, &e_upd);   // :314-316
         n_exps += e_upd;
@@ -448,7 +448,7 @@ template <int NB, int NX, int NY, int LW, bool TM>
 __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, const float* sw, float* rt, float* img,
                                           int wl, int nl, int frame, int lane, uint32_t tmem) {
     using L = Layout<NB>;
-    using I = CoefImg<NB>;
+    using I = CoefImg<NB, Geo<NX>::PANELS>;
     constexpr int P = L::P;
     const bool mine = wl >= 0;
     const uint64_t gid = (uint64_t)(a.id_base + (int64_t)wl * a.id_stride);
@@ -490,7 +490,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
             coef_from_vector<NB>(cf, v, fl, oxd, oyd);
             set_fast_serial<NB, NX, NY>(cf);
             if (NX >= 64 && a.cull) set_cull_serial<NB, NX, NY>(cf); else no_cull<NB, NX, NY>(cf);
-            store_coef<NB>(img + lane * I::STRIDE, cf);
+            store_coef<NB, Geo<NX>::PANELS>(img + lane * I::STRIDE, cf);
         }
         __syncwarp();
 
@@ -499,7 +499,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
 #pragma unroll 1
         for (int i = 0; i < nl; ++i) {
             Coef<NB> cf;
-            load_coef<NB>(cf, img + i * I::STRIDE);
+            load_coef<NB, Geo<NX>::PANELS>(cf, img + i * I::STRIDE);
             unsigned e_upd = 0;
             const double c = warp_chi2<NB, NX, NY, false, true, 1, TM>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd, tmem);   // :314-316
             if (lane == i) { chi_t = c; n_exps += e_upd; }
@@ -546,7 +546,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
 
 template <int NB, int NX, int NY, int NW, int LW>
 __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_constant__ RunArgs a) {
-    using I = CoefImg<NB>;
+    using I = CoefImg<NB, Geo<NX>::PANELS>;
     constexpr int TAB = Scratch<NB, NY>::FLOATS;
     // stamps of up to 64 x 64 pixels also live in the TMEM pixel store (see tmem_fill_stamp)
     constexpr bool TM = Geo<NX>::PANELS == 1 && Rows<NY, 1>::HALVES == 1;
@@ -941,7 +941,9 @@ static int configure_gibbs(lapf_sampler* s) {
     auto kern = gibbs_kernel<NB, NX, NX, NW, MINB, TEAM>;
     s->nw = NW / TEAM;   // walkers per CTA item
     s->minb = MINB;
-    s->smem = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * Scratch<NB, NX, TEAM>::FLOATS;
+    constexpr size_t kBytes = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * Scratch<NB, NX, TEAM>::FLOATS;
+    static_assert(kBytes + 16 * 1024 <= 227 * 1024, "team kernel: shared memory per CTA (dynamic + static scratch)");
+    s->smem = kBytes;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, s->smem));
@@ -965,7 +967,9 @@ static int configure_batch(lapf_sampler* s) {
     s->nw = NW;
     s->chunk = NW * LW;
     s->minb = 1;
-    s->smem = sizeof(float) * (2 * NX * NX + NW * Scratch<NB, NX>::FLOATS + NW * LW * CoefImg<NB>::STRIDE);
+    constexpr size_t kBytes = sizeof(float) * (2 * NX * NX + NW * Scratch<NB, NX>::FLOATS + NW * LW * CoefImg<NB, Geo<NX>::PANELS>::STRIDE);
+    static_assert(kBytes + 256 <= 227 * 1024, "batched kernel: shared memory per CTA");
+    s->smem = kBytes;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, s->smem));
@@ -989,7 +993,7 @@ static int launch_batch(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
         const int nb__ = s->cfg.problem.nbody, nx__ = s->cfg.problem.nx;                    \
         if (nb__ == 2 && nx__ == 32) return FN<2, 32, 16, 32>(__VA_ARGS__);                 \
         if (nb__ == 2 && nx__ == 64) return FN<2, 64, 16, 32>(__VA_ARGS__);                 \
-        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 16, 16>(__VA_ARGS__);               \
+        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 16, 12>(__VA_ARGS__);               \
         if (nb__ == 3 && nx__ == 32) return FN<3, 32, 16, 32>(__VA_ARGS__);                 \
         if (nb__ == 3 && nx__ == 64) return FN<3, 64, 16, 24>(__VA_ARGS__);                 \
         if (nb__ == 3 && nx__ == 128) return FN<3, 128, 12, 16>(__VA_ARGS__);               \

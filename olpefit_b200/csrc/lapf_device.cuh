@@ -149,10 +149,11 @@ struct Coef {
     float x0[K], y0[K], amp[K];   // component 2o = narrow core of object o, 2o+1 = its wide wing
     float sa[2], sb[2], sc[2];    // shape 0 = narrow, 1 = wide; a, b, c of A.1 times -log2(e)
     float floor;
-    // far-field culling (set_cull): row steps [lo, hi] in which a class of components can matter
-    // (class 0 = narrow cores, 1 = wide wings; empty when lo > hi), and the column panels (bit p)
-    int lo[2], hi[2];
-    uint32_t pan[2];
+    // far-field culling (set_cull -> set_segments): per column panel the row steps
+    //   [0, seg0) floor only, [seg0, seg1) wide wings, [seg1, seg2) all, [seg2, seg3) wings, rest floor only
+    // and the component evaluations (pixels x components) they add up to
+    int seg[2][4];
+    unsigned nexp;
     // the factorised pixel loop (row_steps_fast) is safe for this vector (set_fast)
     bool fast;
 };
@@ -226,40 +227,41 @@ __device__ __forceinline__ void load_shape(Coef<NB>& cf, int which, const float*
 // Shared-memory image of a Coef: 16-byte slots, an ODD number of them per walker, so that both the
 // one-walker-per-lane accesses of the batched sampler and its broadcast reads are conflict-free
 // 128-bit transactions.
-template <int NB>
+template <int NB, int PANELS>
 struct CoefImg {
     static constexpr int K = 2 * NB;
-    static constexpr int WORDS = 3 * K + 14;          // x0 y0 amp | sa sb sc floor | lo hi pan fast
+    static constexpr int WORDS = 3 * K + 7 + 4 * PANELS + 2;   // x0 y0 amp | sa sb sc floor | segments | nexp fast
     static constexpr int V4 = ((WORDS + 3) / 4) | 1;
     static constexpr int STRIDE = 4 * V4;             // floats per walker
 };
 
-template <int NB>
+template <int NB, int PANELS>
 __device__ __forceinline__ void store_coef(float* __restrict__ dst, const Coef<NB>& cf) {
     constexpr int K = 2 * NB;
-    using I = CoefImg<NB>;
+    using I = CoefImg<NB, PANELS>;
     float v[I::STRIDE];
 #pragma unroll
     for (int i = 0; i < I::STRIDE; ++i) v[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < K; ++k) { v[k] = cf.x0[k]; v[K + k] = cf.y0[k]; v[2 * K + k] = cf.amp[k]; }
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        v[3 * K + c] = cf.sa[c]; v[3 * K + 2 + c] = cf.sb[c]; v[3 * K + 4 + c] = cf.sc[c];
-        v[3 * K + 7 + c] = __int_as_float(cf.lo[c]); v[3 * K + 9 + c] = __int_as_float(cf.hi[c]);
-        v[3 * K + 11 + c] = __uint_as_float(cf.pan[c]);
-    }
+    for (int c = 0; c < 2; ++c) { v[3 * K + c] = cf.sa[c]; v[3 * K + 2 + c] = cf.sb[c]; v[3 * K + 4 + c] = cf.sc[c]; }
     v[3 * K + 6] = cf.floor;
-    v[3 * K + 13] = __int_as_float(cf.fast ? 1 : 0);
+#pragma unroll
+    for (int p = 0; p < PANELS; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[3 * K + 7 + 4 * p + q] = __int_as_float(cf.seg[p][q]);
+    v[3 * K + 7 + 4 * PANELS] = __uint_as_float(cf.nexp);
+    v[3 * K + 8 + 4 * PANELS] = __int_as_float(cf.fast ? 1 : 0);
 #pragma unroll
     for (int q = 0; q < I::V4; ++q)
         reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
-template <int NB>
+template <int NB, int PANELS>
 __device__ __forceinline__ void load_coef(Coef<NB>& cf, const float* __restrict__ src) {
     constexpr int K = 2 * NB;
-    using I = CoefImg<NB>;
+    using I = CoefImg<NB, PANELS>;
     float v[I::STRIDE];
 #pragma unroll
     for (int q = 0; q < I::V4; ++q) {
@@ -269,13 +271,14 @@ __device__ __forceinline__ void load_coef(Coef<NB>& cf, const float* __restrict_
 #pragma unroll
     for (int k = 0; k < K; ++k) { cf.x0[k] = v[k]; cf.y0[k] = v[K + k]; cf.amp[k] = v[2 * K + k]; }
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        cf.sa[c] = v[3 * K + c]; cf.sb[c] = v[3 * K + 2 + c]; cf.sc[c] = v[3 * K + 4 + c];
-        cf.lo[c] = __float_as_int(v[3 * K + 7 + c]); cf.hi[c] = __float_as_int(v[3 * K + 9 + c]);
-        cf.pan[c] = __float_as_uint(v[3 * K + 11 + c]);
-    }
+    for (int c = 0; c < 2; ++c) { cf.sa[c] = v[3 * K + c]; cf.sb[c] = v[3 * K + 2 + c]; cf.sc[c] = v[3 * K + 4 + c]; }
     cf.floor = v[3 * K + 6];
-    cf.fast = __float_as_int(v[3 * K + 13]) != 0;
+#pragma unroll
+    for (int p = 0; p < PANELS; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cf.seg[p][q] = __float_as_int(v[3 * K + 7 + 4 * p + q]);
+    cf.nexp = __float_as_uint(v[3 * K + 7 + 4 * PANELS]);
+    cf.fast = __float_as_int(v[3 * K + 8 + 4 * PANELS]) != 0;
 }
 
 // Coefficients of a parameter vector given in FP64 frame coordinates, by ONE thread: the same
@@ -480,8 +483,33 @@ __device__ __forceinline__ void cull_one(float a, float x0, float y0, float sa, 
     }
 }
 
+// From the class intervals to the segments of every panel (the wing interval is widened to contain
+// the core interval: evaluating a component where it is not needed is harmless).  The plain loop
+// and team members (whose update time is set by the warp with the busiest rows) evaluate densely.
+// Needs cf.fast.
+template <int NB, int NX, int NY, int TEAM>
+__device__ __forceinline__ void set_segments(Coef<NB>& cf, const int (&lo)[2], const int (&hi)[2], const uint32_t (&pm)[2]) {
+    using G = Geo<NX>;
+    constexpr int STEPS = NY / G::RG;
+    unsigned n = 0;
+#pragma unroll
+    for (int pan = 0; pan < G::PANELS; ++pan) {
+        const bool n_on = ((pm[0] >> pan) & 1u) && lo[0] <= hi[0];
+        const bool w_on = ((pm[1] >> pan) & 1u) && lo[1] <= hi[1];
+        int nlo = n_on ? lo[0] : STEPS, nhi1 = n_on ? hi[0] + 1 : STEPS;
+        int wlo = w_on ? lo[1] : nlo, whi1 = w_on ? hi[1] + 1 : nhi1;
+        wlo = min(wlo, nlo);
+        whi1 = max(whi1, nhi1);
+        if (!n_on) { nlo = whi1; nhi1 = whi1; }
+        if (!cf.fast || TEAM > 1) { wlo = 0; nlo = 0; nhi1 = STEPS; whi1 = STEPS; }
+        cf.seg[pan][0] = wlo; cf.seg[pan][1] = nlo; cf.seg[pan][2] = nhi1; cf.seg[pan][3] = whi1;
+        n += (unsigned)((nhi1 - nlo) + (whi1 - wlo));
+    }
+    cf.nexp = (unsigned)(G::PW * G::RG * NB) * n;
+}
+
 // cooperative form: lane k < K works out component k, the hulls are formed with shuffles
-template <int NB, int NX, int NY>
+template <int NB, int NX, int NY, int TEAM = 1>
 __device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
     using G = Geo<NX>;
     constexpr int K = 2 * NB;
@@ -503,12 +531,15 @@ __device__ __forceinline__ void set_cull(Coef<NB>& cf, int lane) {
         hi = max(hi, __shfl_xor_sync(kFull, hi, off));
         pm |= __shfl_xor_sync(kFull, pm, off);
     }
+    int clo[2], chi[2];
+    uint32_t cpm[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        cf.lo[c] = __shfl_sync(kFull, lo, c);
-        cf.hi[c] = __shfl_sync(kFull, hi, c);
-        cf.pan[c] = __shfl_sync(kFull, pm, c);
+        clo[c] = __shfl_sync(kFull, lo, c);
+        chi[c] = __shfl_sync(kFull, hi, c);
+        cpm[c] = __shfl_sync(kFull, pm, c);
     }
+    set_segments<NB, NX, NY, TEAM>(cf, clo, chi, cpm);
 }
 
 // one-thread form (the batched sampler prepares one walker per lane): same decisions
@@ -516,23 +547,25 @@ template <int NB, int NX, int NY>
 __device__ __forceinline__ void set_cull_serial(Coef<NB>& cf) {
     constexpr int K = 2 * NB;
     constexpr int STEPS = NY / Geo<NX>::RG;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) { cf.lo[c] = STEPS; cf.hi[c] = -1; cf.pan[c] = 0u; }
+    int clo[2] = {STEPS, STEPS}, chi[2] = {-1, -1};
+    uint32_t cpm[2] = {0u, 0u};
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         int lo, hi;
         uint32_t pm;
         cull_one<NX, NY>(cf.amp[k], cf.x0[k], cf.y0[k], cf.sa[k & 1], cf.sb[k & 1], cf.sc[k & 1], cf.floor, lo, hi, pm);
-        cf.lo[k & 1] = min(cf.lo[k & 1], lo);
-        cf.hi[k & 1] = max(cf.hi[k & 1], hi);
-        cf.pan[k & 1] |= pm;
+        clo[k & 1] = min(clo[k & 1], lo);
+        chi[k & 1] = max(chi[k & 1], hi);
+        cpm[k & 1] |= pm;
     }
+    set_segments<NB, NX, NY, 1>(cf, clo, chi, cpm);
 }
 
-template <int NB, int NX, int NY>
+template <int NB, int NX, int NY, int TEAM = 1>
 __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) { cf.lo[c] = 0; cf.hi[c] = NY / Geo<NX>::RG - 1; cf.pan[c] = 0xffffffffu; }
+    const int clo[2] = {0, 0}, chi[2] = {NY / Geo<NX>::RG - 1, NY / Geo<NX>::RG - 1};
+    const uint32_t cpm[2] = {0xffffffffu, 0xffffffffu};
+    set_segments<NB, NX, NY, TEAM>(cf, clo, chi, cpm);
 }
 
 // The factorised pixel loop multiplies factors whose exponents can be large although their sum is
@@ -840,6 +873,7 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
     const int c = lane % G::LPR, g = lane / G::LPR;
     const int swap = (G::PW == 32) ? (g & 1) : 0;
     double acc = 0.0;
+    if (exps) *exps += cf.nexp;
 #pragma unroll 1
     for (int half = 0; half < R::HALVES; ++half) {
         build_row_table<NB, NX, TR, TEAM>(rt, cf, lane, half * TR, tw);
@@ -850,22 +884,16 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
         for (int pan = 0; pan < G::PANELS; ++pan) {
             const int colA = pan * G::PW + 4 * c + (G::PW / 2) * swap;
             const int colB = pan * G::PW + 4 * c + (G::PW / 2) * (1 - swap);
-            // segments of this panel (in row steps of this table):
+            // segments of this panel, clipped to the row steps of this table:
             //   [0,wlo) none, [wlo,nlo) wings, [nlo,nhi1) all, [nhi1,whi1) wings, [whi1,STEPS) none
-            const bool n_on = ((cf.pan[0] >> pan) & 1u) && cf.lo[0] <= cf.hi[0];
-            const bool w_on = ((cf.pan[1] >> pan) & 1u) && cf.lo[1] <= cf.hi[1];
-            const int base = half * STEPS;
-            int nlo = n_on ? min(max(cf.lo[0] - base, 0), STEPS) : STEPS;
-            int nhi1 = n_on ? min(max(cf.hi[0] + 1 - base, 0), STEPS) : STEPS;
-            if (nlo >= nhi1) { nlo = STEPS; nhi1 = STEPS; }
-            int wlo = w_on ? min(max(cf.lo[1] - base, 0), STEPS) : nlo;
-            int whi1 = w_on ? min(max(cf.hi[1] + 1 - base, 0), STEPS) : nhi1;
-            if (w_on && wlo >= whi1) { wlo = nlo; whi1 = nhi1; }
-            wlo = min(wlo, nlo);               // the wing interval is widened to contain the core interval:
-            whi1 = max(whi1, nhi1);            // evaluating a component where it is not needed is harmless
-            if (nlo >= nhi1) { nlo = whi1; nhi1 = whi1; }
-            if (!cf.fast || TEAM > 1) { wlo = 0; nlo = 0; nhi1 = STEPS; whi1 = STEPS; }   // dense
-            if (exps) *exps += (unsigned)(G::PW * G::RG) * (unsigned)((nhi1 - nlo) * NB + (whi1 - wlo) * NB);
+            const bool p1 = G::PANELS > 1 && pan > 0;   // (constant indices keep the coefficients in registers)
+            int wlo = p1 ? cf.seg[1][0] : cf.seg[0][0], nlo = p1 ? cf.seg[1][1] : cf.seg[0][1];
+            int nhi1 = p1 ? cf.seg[1][2] : cf.seg[0][2], whi1 = p1 ? cf.seg[1][3] : cf.seg[0][3];
+            if (R::HALVES > 1) {
+                const int base = half * STEPS;
+                wlo = min(max(wlo - base, 0), STEPS); nlo = min(max(nlo - base, 0), STEPS);
+                nhi1 = min(max(nhi1 - base, 0), STEPS); whi1 = min(max(whi1 - base, 0), STEPS);
+            }
             float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
             if (cf.fast) {
                 LaneK<NB> lk;

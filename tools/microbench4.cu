@@ -5,8 +5,8 @@
 #include "../olpefit_b200/csrc/lapf_device.cuh"
 using namespace lapf;
 
-template <bool TM>
-__global__ void __launch_bounds__(512, 1) pass_kernel(double* out, int passes) {
+template <bool TM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) pass_kernel(double* out, int passes) {
     constexpr int NB = 2, NX = 64, NY = 64;
     extern __shared__ __align__(128) float smem[];
     __shared__ uint32_t tslot;
@@ -57,16 +57,16 @@ __global__ void __launch_bounds__(512, 1) pass_kernel(double* out, int passes) {
     if (TM && warp == 0) tmem_dealloc(tbase, 256);
 }
 
-template <bool TM>
+template <bool TM, int WARPS>
 void run(const char* name, double* d, int sms, int khz) {
     const int smem = (2 * 64 * 64 + 16 * 1920) * 4;
-    cudaFuncSetAttribute(pass_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(pass_kernel<TM, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int passes = 4000;
     float best = 1e30f, ms;
     for (int r = 0; r < 3; ++r) {
         cudaEventRecord(e0);
-        pass_kernel<TM><<<sms, 512, smem>>>(d, passes);
+        pass_kernel<TM, WARPS><<<sms, WARPS * 32, smem>>>(d, passes);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(err)); return; }
@@ -75,14 +75,15 @@ void run(const char* name, double* d, int sms, int khz) {
     }
     double h[17]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     printf("%-6s %.3f ms  %.0f cycles per pass per scheduler  -> %.3e pixel-evals/s  (chi2 sums %.10e %.10e; comp-evals/pass %.0f)\n",
-           name, best, best * 1e-3 * khz * 1e3 / (4.0 * passes), (double)sms * 16 * passes * 4096 / (best * 1e-3), h[0], h[15], h[16]);
+           name, best, best * 1e-3 * khz * 1e3 / ((WARPS / 4.0) * passes), (double)sms * WARPS * passes * 4096 / (best * 1e-3), h[0], h[7], h[16]);
 }
 
 int main() {
     int sms = 0, khz = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
     double* d; cudaMalloc(&d, 17 * 8);
-    run<false>("smem", d, sms, khz);
-    run<true>("tmem", d, sms, khz);
+    run<true, 16>("tmem16", d, sms, khz);
+    run<true, 12>("tmem12", d, sms, khz);
+    run<true, 8>("tmem8", d, sms, khz);
     return 0;
 }
