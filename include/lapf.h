@@ -40,6 +40,11 @@ extern "C" {
 /* lapf_problem.flags: evaluate every component at every pixel, also where its value is provably
  * below 2^-24 of the floor (default: such far-field rows are skipped; results agree to FP32 rounding) */
 #define LAPF_FLAG_NO_CULL 1
+/* lapf_problem.flags: always take the plain pixel loop (one exponential per pixel and component)
+ * instead of the factorised one (one exponential per 4-pixel group and component).
+ * The factorised loop falls back to the plain one by itself for vectors outside its safe range;
+ * this switch exists to compare the two. */
+#define LAPF_FLAG_PLAIN_LOOP 2
 
 typedef enum lapf_status {
     LAPF_OK = 0,
@@ -59,7 +64,7 @@ typedef struct lapf_problem {
     int32_t floor_index;    /* parameter slot added as the constant floor: 12 reproduces the
                                reference for both layouts (apf_step2.py:120 -- sigmax2 --
                                and 3body/apf_step2_3body.py:121 -- bkgd) */
-    int32_t flags;          /* 0, or LAPF_FLAG_NO_CULL */
+    int32_t flags;          /* 0, or LAPF_FLAG_NO_CULL | LAPF_FLAG_PLAIN_LOOP */
     const float* data;      /* device [F][ny][nx]; finite everywhere (0 on masked pixels) */
     const float* weight;    /* device [F][ny][nx] */
     const int32_t* origin;  /* device [F][2]: frame coordinates (x0, y0) of pixel [0][0] */

@@ -84,6 +84,7 @@ struct ProbPtrs {
     const double* outside;   // [F][3] or nullptr (see lapf_problem.outside)
     int n_frames, floor_index;
     int cull;                // far-field culling on/off
+    int plain;               // always the plain pixel loop
 };
 
 // chi-square of the image pixels outside the cut-out, where the model is the constant floor f
@@ -116,6 +117,7 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
     load_shape<NB>(cf, 1, tf[warp]);
     __shared__ __align__(16) float rt[4][Scratch<NB, NY>::FLOATS];
     set_fast<NB, NX, NY>(cf, lane);
+    if (pr.plain) cf.fast = false;
     if (NX >= 64 && pr.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
     const size_t off = (size_t)f * NX * NY;
     double chi = warp_chi2<NB, NX, NY, STORE, false>(cf, rt[warp], pr.data + off, pr.weight + off,
@@ -248,7 +250,7 @@ struct RunArgs {
     uint64_t seed;
     double widths[LAPF_MAX_PARAMS];
     uint32_t log_mask;
-    int thin, floor_index, n_items, cull;
+    int thin, floor_index, n_items, cull, plain;
 };
 
 // One walker for n_updates updates.  TEAM = 1: one warp does everything.  TEAM > 1 (few walkers,
@@ -337,6 +339,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
             }
         }
         set_fast<NB, NX, NY>(cf, lane);
+        if (a.plain) cf.fast = false;
         // in a team the update time is set by the warp with the busiest rows: culling cannot help there
         if (NX >= 64 && TEAM == 1 && a.cull) set_cull<NB, NX, NY, TEAM>(cf, lane); else no_cull<NB, NX, NY, TEAM>(cf);
         unsigned e_upd = 0;
@@ -489,6 +492,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
             Coef<NB> cf;
             coef_from_vector<NB>(cf, v, fl, oxd, oyd);
             set_fast_serial<NB, NX, NY>(cf);
+            if (a.plain) cf.fast = false;
             if (NX >= 64 && a.cull) set_cull_serial<NB, NX, NY>(cf); else no_cull<NB, NX, NY>(cf);
             store_coef<NB, Geo<NX>::PANELS>(img + lane * I::STRIDE, cf);
         }
@@ -814,6 +818,10 @@ static int cull_enabled(const lapf_problem* p) {
     return p->nx >= 64 ? 1 : 0;
 }
 
+static int plain_loop(const lapf_problem* p) {
+    return ((p->flags & LAPF_FLAG_PLAIN_LOOP) || getenv("LAPF_PLAIN_LOOP")) ? 1 : 0;
+}
+
 static bool stamp_supported(int ny, int nx) { return ny == nx && (nx == 32 || nx == 64 || nx == 128); }
 
 static int check_problem(const lapf_problem* p) {
@@ -903,7 +911,7 @@ int lapf_model_chi2(const lapf_problem* prob, const double* params, int64_t B, c
     if ((rc = require_device())) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     ProbPtrs pr{prob->data, prob->weight, prob->origin, prob->outside, prob->n_frames, prob->floor_index,
-                cull_enabled(prob)};
+                cull_enabled(prob), plain_loop(prob)};
     if (stamp_supported(prob->ny, prob->nx) && (!model_out || ((uintptr_t)model_out & 15) == 0)) {
         if (prob->nbody == 2)
             launch_stamp_k1_size<2>(prob->nx, model_out != nullptr, pr, params, B, frame_of, model_out, chi2_out, st);
@@ -1281,6 +1289,7 @@ int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int6
     a.log_mask = s->log_mask;
     a.thin = s->cfg.thin; a.floor_index = pb.floor_index; a.n_items = s->n_items;
     a.cull = cull_enabled(&pb);
+    a.plain = plain_loop(&pb);
     int rc = launch_dispatch(s, a, (cudaStream_t)stream);
     if (rc) return rc;
     s->count += n_updates;

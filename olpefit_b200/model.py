@@ -25,7 +25,7 @@ class PixelDomain:
     the frame coordinates of pixel [0][0] of each frame."""
 
     def __init__(self, data, weight, origin=None, nbody=2, floor_index=None, device="cuda", outside=None,
-                 cull=True):
+                 cull=True, plain_loop=False):
         _lib.load()
         if not torch.cuda.is_available():
             raise _lib.LapfError("no CUDA device: olpefit_b200 has no CPU path")
@@ -46,7 +46,7 @@ class PixelDomain:
         self.nbody = int(nbody)
         self.nparam = layout.nparam(self.nbody)
         self.floor_index = layout.REFERENCE_FLOOR_INDEX if floor_index is None else int(floor_index)
-        self.flags = 0 if cull else 1          # LAPF_FLAG_NO_CULL
+        self.flags = (0 if cull else 1) | (2 if plain_loop else 0)   # LAPF_FLAG_NO_CULL, LAPF_FLAG_PLAIN_LOOP
         # optional [F, 3] float64: sum w, sum w d, sum w d^2 over the image pixels outside the cut-outs
         self.outside = None
         if outside is not None:

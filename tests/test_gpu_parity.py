@@ -549,3 +549,124 @@ def test_error_paths_on_device(gpu):
     _, c = dom.model_chi2(np.stack([p0, p0, p0]), frame_of=np.array([0, 7, 1], dtype=np.int32))
     c = c.cpu().numpy()
     assert np.isfinite(c[0]) and np.isnan(c[1]) and np.isfinite(c[2])
+
+
+# ---------------------------------------------------------------------------------------------
+# factorised pixel loop, TMEM pixel store, batched sampler
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nbody,size", [(2, 32), (2, 64), (3, 64), (2, 128), (3, 32)])
+def test_factorised_loop_agrees_with_plain_loop(gpu, nbody, size):
+    """The factorised pixel loop (one exponential per 4-pixel group and component, DESIGN.md
+    section 4) against the plain loop (one per pixel and component) on the same vectors: both are
+    within the stated 1e-5 of the float64 oracle, they agree with each other to FP32 rounding, and
+    a sampler forced onto the plain loop follows the same chain."""
+    synth, model = gpu["synth"], gpu["model"]
+    lay = orc.layout_for(nbody)
+    ox, oy = synth.stamp_origin(size)
+    img, truth = synth.make_frame(4, nbody, region=(oy, oy + size, ox, ox + size))
+    fast = _domain(gpu, img, (ox, oy), nbody)
+    plain = model.PixelDomain(fast.data, fast.weight, fast.origin, nbody=nbody, plain_loop=True)
+    tl = truth.copy()
+    tl[0:2 * nbody:2] -= ox
+    tl[1:2 * nbody:2] -= oy
+    vecs = _random_vectors(tl, nbody, 32, np.random.default_rng(100 * size + nbody))
+    vecs[:, 0:2 * nbody:2] += ox
+    vecs[:, 1:2 * nbody:2] += oy
+    m_f, c_f = (t.cpu().numpy() for t in fast.model_chi2(vecs, want_model=True))
+    m_p, c_p = (t.cpu().numpy() for t in plain.model_chi2(vecs, want_model=True))
+    assert np.max(np.abs(m_f - m_p) / np.abs(m_p)) < 5e-6
+    np.testing.assert_allclose(c_f, c_p, rtol=2e-6)
+    for i in (0, 7, 19):
+        m = orc.model_image(vecs[i], lay, size, size, origin=(ox, oy))
+        assert np.max(np.abs(m_f[i] - m) / np.abs(m)) < RTOL and np.max(np.abs(m_p[i] - m) / np.abs(m)) < RTOL
+    # chains: same stream, same decisions until FP32 rounding flips a borderline accept
+    init = np.tile(truth.astype(np.float32).astype(np.float64), (5, 1))
+    out = []
+    for dom in (fast, plain):
+        with gpu["sampler"].GibbsSampler(dom, init, seed=21) as s:
+            out.append(s.run(120).cpu().numpy())
+    np.testing.assert_allclose(out[0][:40, :, :-1], out[1][:40, :, :-1], rtol=1e-9)
+    np.testing.assert_allclose(out[0][:40, :, -1], out[1][:40, :, -1], rtol=2e-6)
+    assert np.mean(np.isclose(out[0][..., :-1], out[1][..., :-1], rtol=1e-9)) > 0.9
+
+
+def test_wild_vectors_leave_the_factorised_loop(gpu):
+    """Outside its safe range (factors that would overflow or underflow on their own) the
+    factorised loop hands the vector to the plain loop: needle-sharp cores, sources far outside
+    the stamp, amplitudes enormous against the floor, elongated rotated profiles.  All of them still
+    match the float64 oracle to the stated tolerance.  (Axis ratios beyond ~8 at 45 degrees do not, in
+    either loop: the FP32 quadratic form cancels there, 2e-5 at 11:1 -- DESIGN.md section 5.)"""
+    synth = gpu["synth"]
+    lay = orc.layout_for(2)
+    size = 64
+    ox, oy = synth.stamp_origin(size)
+    img, truth = synth.make_frame(6, 2, region=(oy, oy + size, ox, ox + size))
+    dom = gpu["frame"].prepare_domain(img, HEADER, origin=(ox, oy), nbody=2, floor_index=9)
+    t = truth.astype(np.float32).astype(np.float64)
+    vecs = []
+    v = t.copy(); v[10] = 0.35; v[11] = 0.4; vecs.append(v)                    # needle core (sigma 0.35 px)
+    v = t.copy(); v[0] -= 300.0; vecs.append(v)                                 # star 300 px left of the stamp
+    v = t.copy(); v[3] += 2000.0; vecs.append(v)                                # companion far above it
+    v = t.copy(); v[9] = 1e-4; vecs.append(v)                                   # floor tiny against the amplitudes
+    v = t.copy(); v[6] = 3e13; vecs.append(v)                                   # enormous amplitude
+    v = t.copy(); v[10] = 0.6; v[11] = 1.8; v[14] = 0.78; vecs.append(v)        # sharp 3:1 core at 45 degrees
+    v = t.copy(); v[12] = 9.0; v[13] = 2.2; v[15] = -0.7; vecs.append(v)        # elongated 4:1 wing
+    v = t.copy(); v[10] = 0.05; vecs.append(v)                                  # sub-pixel delta
+    vecs = np.array(vecs).astype(np.float32).astype(np.float64)
+    model, chi2 = dom.model_chi2(vecs, want_model=True)
+    model, chi2 = model.cpu().numpy(), chi2.cpu().numpy()
+    img64 = img.astype(np.float64)
+    w = orc.weight_map(img64, HEADER)
+    for i, q in enumerate(vecs):
+        m = orc.model_image(q, lay, size, size, origin=(ox, oy), floor_index=9)
+        rel = np.max(np.abs(model[i] - m) / np.abs(m))
+        assert rel < RTOL, "vector %d: %.2e" % (i, rel)
+        assert chi2[i] == pytest.approx(orc.chi_squared_weighted(img64, m, w), rel=RTOL)
+    # and a chain started from a wild point is the chain the plain loop gives, bit for bit
+    plain = gpu["model"].PixelDomain(dom.data, dom.weight, dom.origin, nbody=2, floor_index=9, plain_loop=True)
+    res = []
+    for d in (dom, plain):
+        with gpu["sampler"].GibbsSampler(d, vecs[:1], seed=2) as s:
+            res.append(s.run(30))
+    assert gpu["torch"].equal(res[0], res[1])
+
+
+def test_batched_sampler_partitions(gpu):
+    """The batched kernel deals walkers to CTAs, warps and lanes: ragged frames, frames without
+    walkers, fewer walkers than SMs, more walkers of one frame than a CTA holds at once.  Whatever
+    the shape, a walker's chain is the chain it has when it runs alone under the same id."""
+    torch = gpu["torch"]
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 32, n_frames=7)
+    rng = np.random.default_rng(8)
+
+    def solo(frame, gid, start, n_upd, seed):
+        with gpu["sampler"].GibbsSampler(dom, start[None], np.array([frame], dtype=np.int32), seed=seed,
+                                         id_base=gid) as s:
+            return s.run(n_upd)[:, 0]
+
+    # ragged: 7 frames with very different walker counts (one of them empty), distinct starting points
+    counts = [1, 40, 3, 0, 600, 2, 33]
+    frame_of = np.repeat(np.arange(7), counts).astype(np.int32)
+    rng.shuffle(frame_of)
+    W = frame_of.size
+    init = np.tile(p0, (W, 1))
+    init[:, 0:4] += rng.normal(0, 0.05, (W, 4))
+    init = init.astype(np.float32).astype(np.float64)
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, seed=12, id_base=1000) as s:
+        chain = s.run(24)
+        st, tries, acc = s.state()
+    assert bool((tries.sum(dim=1) == 24).all())
+    for w in (0, 1, 17, 333, W - 1, int(np.flatnonzero(frame_of == 0)[0]), int(np.flatnonzero(frame_of == 5)[1])):
+        assert torch.equal(chain[:, w], solo(int(frame_of[w]), 1000 + w, init[w], 24, 12)), "walker %d" % w
+
+    # more walkers of one frame than a CTA holds at once (and a few of another frame)
+    W = 90000
+    frame_of = np.zeros(W, dtype=np.int32)
+    frame_of[-37:] = 2
+    init = np.tile(p0, (W, 1))
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, seed=5) as s:
+        chain = s.run(3)
+        st, tries, acc = s.state()
+    assert bool((tries.sum(dim=1) == 3).all())
+    for w in (0, 511, 512, 607, 608, 44444, W - 38, W - 1):
+        assert torch.equal(chain[:, w], solo(int(frame_of[w]), w, init[w], 3, 5)), "walker %d" % w
