@@ -190,12 +190,30 @@ def prepare_domain(frames, header, size=None, cut=None, origin=None, nbody=2, fl
         return np.ascontiguousarray(np.broadcast_to(a.reshape(-1, 2), (nf, 2)))
 
     cut_np, org_np = pairs(cut), pairs(origin)
-    cut_t = torch.as_tensor(cut_np.astype(np.int32)).to(dev)
     if into is not None:
         if (into.n_frames, into.ny, into.nx) != (nf, ny, nx):
             raise ValueError("into has shape %s, new frames give %s" % ((into.n_frames, into.ny, into.nx), (nf, ny, nx)))
         data, weight = into.data, into.weight
+        # cut-out positions and origins travel through a small pinned staging buffer kept on the
+        # domain, and only when they changed: a pageable copy here would make the host wait for the
+        # stream and serialise a stream of batches (bench.py e2e, ChainStreamer)
+        new = np.stack([cut_np, org_np + cut_np]).astype(np.int32)
+        st = getattr(into, "_stage", None)
+        if st is None:
+            st = {"host": torch.empty((2, nf, 2), dtype=torch.int32).pin_memory(),
+                  "cut": torch.empty((nf, 2), dtype=torch.int32, device=dev),
+                  "event": torch.cuda.Event(), "valid": False}
+            into._stage = st
+        if not (st["valid"] and np.array_equal(st["host"].numpy(), new)):
+            st["event"].synchronize()            # the previous upload has left the staging buffer
+            st["host"].numpy()[...] = new
+            st["cut"].copy_(st["host"][0], non_blocking=True)
+            into.origin.copy_(st["host"][1], non_blocking=True)
+            st["event"].record(torch.cuda.current_stream(dev))
+            st["valid"] = True
+        cut_t = st["cut"]
     else:
+        cut_t = torch.as_tensor(cut_np.astype(np.int32)).to(dev)
         data = torch.empty((nf, ny, nx), dtype=torch.float32, device=dev)
         weight = torch.empty_like(data)
     _lib.check(lib.lapf_frame_prep(fr.data_ptr(), nf, fy, fx, cut_t.data_ptr(), ny, nx,
@@ -217,7 +235,6 @@ def prepare_domain(frames, header, size=None, cut=None, origin=None, nbody=2, fl
 
         outside = sums(d_all, w_all) - sums(data, weight)
     if into is not None:
-        into.origin.copy_(torch.as_tensor((org_np + cut_np).astype(np.int32)))
         if outside is not None:
             if into.outside is None:
                 raise ValueError("into was created without whole_frame=True")

@@ -15,9 +15,11 @@ for c in cases:
     except Exception:
         print("FAILED", c, r.stderr[-400:]); continue
     row = {"args": c, "pixel_evals_per_s": d["value"], "updates_per_s": d["gibbs_updates_per_sec"],
-           "ms_per_step": d["ms_per_step"], "sfu_frac_algorithmic": d["roofline"]["frac"],
-           "sfu_frac_executed": d["roofline"]["frac_executed"], "clocks": d["clocks"]}
+           "ms_per_step": d["ms_per_step"], "fp32_frac_algorithmic": d["roofline"]["frac"],
+           "fp32_frac_executed": d["roofline"]["executed"]["frac"], "sfu_frac_algorithmic": d["roofline"]["sfu"]["frac"],
+           "component_evals_per_pixel_eval": d["roofline"]["executed"]["component_evals_per_pixel_eval"],
+           "clocks": d["clocks"]}
     out.append(row)
-    print("%-75s px/s %.3e upd/s %.3e alg %.3f exec %.3f" % (c, row["pixel_evals_per_s"], row["updates_per_s"],
-          row["sfu_frac_algorithmic"], row["sfu_frac_executed"]), flush=True)
+    print("%-75s px/s %.3e upd/s %.3e fp32 alg %.3f exec %.3f sfu alg %.3f" % (c, row["pixel_evals_per_s"], row["updates_per_s"],
+          row["fp32_frac_algorithmic"], row["fp32_frac_executed"], row["sfu_frac_algorithmic"]), flush=True)
 json.dump(out, open("gpurun_out/sweep.json", "w"), indent=1)
