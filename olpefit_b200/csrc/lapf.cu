@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
 // and at most one written per update).  The arithmetic per walker is the one of run_walker: chains
 // are bit-identical between the two forms.
 // ---------------------------------------------------------------------------------------------
-template <int NB, int NX, int NY, int LW, bool TM>
+template <int NB, int NX, int NY, int LW, int TM>
 __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, const float* sw, float* rt, float* img,
                                           int wl, int nl, int frame, int lane, uint32_t tmem) {
     using L = Layout<NB>;
@@ -553,8 +553,9 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
     using I = CoefImg<NB, Geo<NX>::PANELS>;
     constexpr int TAB = Scratch<NB, NY>::FLOATS;
     // stamps of up to 64 x 64 pixels also live in the TMEM pixel store (see tmem_fill_stamp)
-    constexpr bool TM = Geo<NX>::PANELS == 1 && Rows<NY, 1>::HALVES == 1;
-    constexpr uint32_t TM_COLS = TM ? 16 * (NY / Geo<NX>::RG) : 32;
+    // (128 x 128: the weight plane only, the data plane is read from shared memory)
+    constexpr int TM = (Geo<NX>::PANELS == 1 && Rows<NY, 1>::HALVES == 1) ? 1 : 2;
+    constexpr uint32_t TM_COLS = TM == 1 ? 16 * (NY / Geo<NX>::RG) : 512;
     static_assert(TM_COLS >= 32 && TM_COLS <= 512 && (TM_COLS & (TM_COLS - 1)) == 0, "TMEM allocations are powers of two");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
@@ -591,8 +592,9 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
             cur_frame = f;
             prep_stamp(sd, sw, NX * NY);            // (d, w) -> (d*sqrt(w), -sqrt(w)), once per staged frame
             __syncthreads();
-            if constexpr (TM) {
-                if (warp < 4) tmem_fill_stamp<NX, NY>(tmem_base, sd, sw, warp, lane);
+            {
+                if constexpr (TM == 1) { if (warp < 4) tmem_fill_stamp<NX, NY>(tmem_base, sd, sw, warp, lane); }
+                else { if (warp < 4) tmem_fill_weights<NX, NY>(tmem_base, sw, warp, lane); }
                 tmem_fence_before_sync();
                 __syncthreads();
                 tmem_fence_after_sync();

@@ -137,6 +137,22 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t addr, uint32_t (&r)[16]
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(addr));
 }
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                   "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t addr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld8_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
 // the operands tie every later use of the registers to the wait
 __device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -777,7 +793,7 @@ __device__ __forceinline__ void coop_consts(LaneK<NB>& lk, float* __restrict__ c
     }
 }
 
-template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND, bool TM = false>
+template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND, int TM = 0>
 __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<NB>& lk, float2& s0, float2& s1,
                                                int& i, int i1, StepPtrs& sp, int colA, int colB) {
     using G = Geo<NX>;
@@ -792,8 +808,12 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
     for (; i < i1; ++i) {
         float4 dA, dB, wA, wB;
         uint32_t tv[16];
-        if (TM) {
+        if (TM == 1) {
             tmem_ld16_issue(tm, tv);
+        } else if (TM == 2) {
+            tmem_ld8_issue(tm, tv);
+            dA = *reinterpret_cast<const float4*>(dp + colA);
+            dB = *reinterpret_cast<const float4*>(dp + colB);
         } else {
             dA = *reinterpret_cast<const float4*>(dp + colA);
             dB = *reinterpret_cast<const float4*>(dp + colB);
@@ -835,13 +855,18 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
                 m[2] = __ffma2_rn(make_float2(RB.x, RB.y), u[2], m[2]); m[3] = __ffma2_rn(make_float2(RB.z, RB.w), u[3], m[3]);
             }
         }
-        if (TM) {
+        if (TM == 1) {
             tmem_ld16_wait(tv);
             dA = make_float4(__uint_as_float(tv[0]), __uint_as_float(tv[1]), __uint_as_float(tv[2]), __uint_as_float(tv[3]));
             dB = make_float4(__uint_as_float(tv[4]), __uint_as_float(tv[5]), __uint_as_float(tv[6]), __uint_as_float(tv[7]));
+            tm += 16;
+        } else if (TM == 2) {
+            tmem_ld8_wait(tv);
+            tm += 8;
+        }
+        if (TM) {
             wA = make_float4(__uint_as_float(tv[8]), __uint_as_float(tv[9]), __uint_as_float(tv[10]), __uint_as_float(tv[11]));
             wB = make_float4(__uint_as_float(tv[12]), __uint_as_float(tv[13]), __uint_as_float(tv[14]), __uint_as_float(tv[15]));
-            tm += 16;
         }
         finish_step<NX, STORE, PREP>(m, dA, dB, wA, wB, mp, colA, colB, s0, s1);
         if (STORE) mp += G::RG * NX;
@@ -857,7 +882,7 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
 // order).  Builds the row and column tables in `scratch` (Scratch<NB, NY, TEAM>::FLOATS floats of
 // this warp's own shared memory) itself.  `exps` counts the component evaluations (pixels x
 // components) the far-field culling left to do.
-template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1, bool TM = false>
+template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1, int TM = 0>
 __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restrict__ scratch,
                                             const float* __restrict__ d, const float* __restrict__ w,
                                             float* __restrict__ model_out, int lane, int tw = 0,
@@ -868,8 +893,9 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
     constexpr int K = 2 * NB;
     constexpr int TR = R::TR;
     constexpr int STEPS = TR / G::RG;            // row steps per table (per panel)
-    static_assert(!TM || (TEAM == 1 && PREP && R::HALVES == 1 && G::PANELS == 1),
-                  "the TMEM pixel store holds whole prepared stamps of up to 64 x 64 pixels");
+    static_assert(TM == 0 || (TEAM == 1 && PREP), "the TMEM pixel store holds prepared stamps for whole-warp passes");
+    static_assert(TM != 1 || (R::HALVES == 1 && G::PANELS == 1), "both planes fit the 512 TMEM columns up to 64 x 64 pixels");
+    constexpr int TM_STEP = TM == 1 ? 16 : 8;     // TMEM columns per row step
     static_assert(TR % G::RG == 0, "unsupported stamp height");
     static_assert(STEPS % TEAM == 0, "team size must divide the row steps");
     float* rt = scratch;
@@ -904,7 +930,8 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
                 coop_consts<NB, NX>(lk, ct, cf, lane, pan, colA, colB);
                 if (TEAM == 1) {
                     // contiguous steps: the pointers run through the segments
-                    StepPtrs sp{rt + g * T::RS, dh + g * NX, wh + g * NX, STORE ? mh + g * NX : nullptr, tmem};
+                    StepPtrs sp{rt + g * T::RS, dh + g * NX, wh + g * NX, STORE ? mh + g * NX : nullptr,
+                                tmem + (uint32_t)((half * G::PANELS + pan) * STEPS * TM_STEP)};
                     int i = 0;
                     if (NX < 64) {
                         // 32-pixel stamps have no far field (set_cull is never called for them)
@@ -974,6 +1001,34 @@ __device__ __forceinline__ void tmem_fill_stamp(uint32_t tmem_base, const float*
         const float4 wB = *reinterpret_cast<const float4*>(sw + r * NX + colB);
         const float v[16] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w, wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
         tmem_st16(addr + 16 * i, v);
+    }
+    tmem_wait_st();
+}
+
+// 128-pixel stamps: only the weight plane fits (8 columns per row step, 4 tables x 2 panels x 8
+// steps = 512 columns, the whole TMEM); the data plane stays in shared memory.  Same order as the
+// loop nest of warp_chi2: table, panel, row step.
+template <int NX, int NY>
+__device__ __forceinline__ void tmem_fill_weights(uint32_t tmem_base, const float* __restrict__ sw, int warp, int lane) {
+    using G = Geo<NX>;
+    using R = Rows<NY, 1>;
+    constexpr int STEPS = R::TR / G::RG;
+    static_assert(R::HALVES * G::PANELS * STEPS * 8 <= 512, "weight plane exceeds the TMEM columns");
+    const int c = lane % G::LPR, g = lane / G::LPR;
+    const int swap = (G::PW == 32) ? (g & 1) : 0;
+    const uint32_t addr = tmem_base + ((uint32_t)(32 * warp) << 16);
+#pragma unroll 1
+    for (int hp = 0; hp < R::HALVES * G::PANELS; ++hp) {
+        const int half = hp / G::PANELS, pan = hp % G::PANELS;
+        const int colA = pan * G::PW + 4 * c + (G::PW / 2) * swap, colB = pan * G::PW + 4 * c + (G::PW / 2) * (1 - swap);
+#pragma unroll 1
+        for (int i = 0; i < STEPS; ++i) {
+            const int r = half * R::TR + i * G::RG + g;
+            const float4 wA = *reinterpret_cast<const float4*>(sw + r * NX + colA);
+            const float4 wB = *reinterpret_cast<const float4*>(sw + r * NX + colB);
+            const float v[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+            tmem_st8(addr + (uint32_t)((hp * STEPS + i) * 8), v);
+        }
     }
     tmem_wait_st();
 }
