@@ -123,11 +123,14 @@ def run(kind, nbody, argv=None):
     say("Random seed:", seed)
     if n_local == 0:
         say("rank has no walkers")
-    # Few walkers: several warps per walker, so one update takes 1/16 of the time.  The choice
-    # depends on the TOTAL walker count only, so every rank makes the same one.
+    # Few walkers: several warps per walker, so one update takes a fraction of the time; from about
+    # 1,800 walkers per GPU the batched kernel (a warp owns 32 walkers) is faster (measured on B200:
+    # 64 walkers 3.5e7 / 2.9e7 / 1.4e7 updates/s with 16 / 4 / 1 warps per walker, 592 walkers
+    # 0.8e8 / 2.6e8 / 1.3e8, 2,048 walkers 0.8e8 / 2.2e8 / 2.4e8).  The choice depends on the TOTAL
+    # walker count only, so every rank makes the same one.
     team = args.team
     if team == 0:
-        team = 16 if (total_walkers <= 1200 * world and args.stamp >= 64) else (4 if total_walkers <= 4800 * world else 1)
+        team = 16 if (total_walkers <= 220 * world and args.stamp >= 64) else (4 if total_walkers <= 1800 * world else 1)
     sam = smp.GibbsSampler(dom, np.tile(parameters, (max(n_local, 1), 1)), seed=seed, burn_in=burn_in,
                            thin=args.thin, id_base=id_base, id_stride=id_stride, team_warps=team)
     st0, _, _ = sam.state()
