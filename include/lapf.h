@@ -91,7 +91,9 @@ typedef struct lapf_config {
                                    (apf_step2.py:234 / 3body:220-238) */
     int64_t burn_in;            /* chain rows are produced once count >= burn_in (apf_step2.py:342) */
     int32_t thin;               /* keep every thin-th row after burn-in (1 = reference) */
-    int32_t team_warps;         /* warps cooperating on one walker: 0 = choose automatically */
+    int32_t team_warps;         /* 0 or 1: batched kernel, a warp owns up to 32 walkers (throughput);
+                                   4 or 16: that many warps cooperate on ONE walker (latency, for the
+                                   reference's 24-64 walkers; 16 needs stamps of 64 or 128 pixels) */
 } lapf_config;
 
 typedef struct lapf_sampler lapf_sampler;
@@ -156,8 +158,9 @@ int lapf_sampler_state(lapf_sampler* s, double* state_out, uint32_t* tries_out,
 /* K4 -- batch statistics, written to device memory:
  *   totals_out  device int64[2P+2]: sum over walkers of tries[P], accepts[P], then the minimum
  *               over walkers and parameters of tries (stop rule of apf_step2.py:300, globalised),
- *               then the number of exponentials the sampler really evaluated so far (what is
- *               left of ny*nx*K per update after far-field culling; roofline accounting)
+ *               then the number of component evaluations (pixels x Gaussian components) the
+ *               sampler really did so far (what is left of ny*nx*K per update after far-field
+ *               culling; roofline accounting)
  *   moments_out device double[F][P+1][4] or NULL: per frame and column, over that frame's
  *               walkers and the rows recorded so far: a reference value r, sum of (chain mean - r),
  *               sum of (chain mean - r)^2, sum of chain variances -- the ingredients of the

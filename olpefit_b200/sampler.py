@@ -146,7 +146,7 @@ class GibbsSampler:
 
     def stats(self, moments=True):
         """Batch statistics reduced on the device (K4).  Returns a dict of device tensors:
-        tries[P], accepts[P], min_tries (scalar), exps (scalar: exponentials really evaluated),
+        tries[P], accepts[P], min_tries (scalar), exps (scalar: component evaluations, pixels x Gaussian components, really done),
         moments [F, P+1, 4] (reference, sum of centred chain means, of their squares, of chain
         variances), walkers_per_frame [F], rows (scalar)."""
         dev = self.domain.device
