@@ -1003,9 +1003,9 @@ static int launch_batch(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
         const int nb__ = s->cfg.problem.nbody, nx__ = s->cfg.problem.nx;                    \
         if (nb__ == 2 && nx__ == 32) return FN<2, 32, 16, 32>(__VA_ARGS__);                 \
         if (nb__ == 2 && nx__ == 64) return FN<2, 64, 16, 32>(__VA_ARGS__);                 \
-        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 16, 12>(__VA_ARGS__);               \
+        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 16, 15>(__VA_ARGS__);               \
         if (nb__ == 3 && nx__ == 32) return FN<3, 32, 16, 32>(__VA_ARGS__);                 \
-        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 16, 24>(__VA_ARGS__);                 \
+        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 16, 28>(__VA_ARGS__);                 \
         if (nb__ == 3 && nx__ == 128) return FN<3, 128, 12, 16>(__VA_ARGS__);               \
         return fail(LAPF_ERR_INVALID, "unsupported sampler shape nbody=%d nx=%d", nb__, nx__); \
     } while (0)
