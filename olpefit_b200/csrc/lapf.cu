@@ -57,6 +57,23 @@ static int require_device() {
     return LAPF_OK;
 }
 
+// liblapf takes its few temporaries (initial chi-squares, tile partials) from the device's default
+// stream-ordered pool.  By default that pool hands everything back to the driver at every
+// synchronisation and re-allocates on the next call -- milliseconds, now and then hundreds of them,
+// in the middle of a stream of batches.  Keep the memory in the pool instead.
+static void keep_pool_memory() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    done[dev] = true;
+}
+
 // reference tables: apf_step2.py:215-217,234 and 3body/apf_step2_3body.py:220-238,292-295
 static const double kWidths2[16] = {0.01, 0.01, 0.3, 0.3, 0.08, 0.09, 0.0025, 0.02,
                                     0.001, 0.0008, 0.002, 0.002, 0.001, 0.001, 0.008, 0.01};
@@ -911,6 +928,7 @@ int lapf_model_chi2(const lapf_problem* prob, const double* params, int64_t B, c
     if (B < 0 || (B > 0 && !params)) return fail(LAPF_ERR_INVALID, "params is NULL or B < 0");
     if (B == 0) return LAPF_OK;
     if ((rc = require_device())) return rc;
+    keep_pool_memory();
     cudaStream_t st = (cudaStream_t)stream;
     ProbPtrs pr{prob->data, prob->weight, prob->origin, prob->outside, prob->n_frames, prob->floor_index,
                 cull_enabled(prob), plain_loop(prob)};
