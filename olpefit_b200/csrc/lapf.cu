@@ -2,7 +2,10 @@
 //
 // Kernels
 //   K1  model_chi2_stamp_kernel / model_chi2_generic_kernel   stateless model + chi-square
-//   K2  gibbs_kernel        persistent sampler: a CTA owns a staged stamp, each warp a walker
+//   K2  gibbs_batch_kernel  persistent sampler: a CTA owns a staged stamp (shared memory + TMEM),
+//                           each warp up to 32 walkers (scalar work one walker per lane, pixel
+//                           passes by the whole warp)
+//       gibbs_kernel        4 or 16 warps per walker, for small batches
 //   K4  totals_kernel / moments_kernel                         batch statistics
 //   --  frame_prep_kernel, pack_state_kernel, peak_*_kernel
 //

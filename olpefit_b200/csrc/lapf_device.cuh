@@ -1,9 +1,13 @@
 // Device-side building blocks of the LAPF step-2 hot path for sm_100a.
 //
 //   Layout<NB>      parameter-vector index map (apf_step2.py:108; 3body/apf_step2_3body.py:266-288)
-//   Coef<NB>        per-proposal coefficients of the K = 2*NB elliptical Gaussians
+//   Coef<NB>        per-proposal coefficients of the K = 2*NB elliptical Gaussians, culling
+//                   segments, safe-range flag; CoefImg its shared-memory image
 //   warp_chi2<>     fused model / residual / square / reduce over one stamp by ONE warp
-//                   (replaces build_analytical_model + chi_squared, apf_step2.py:78-137)
+//                   (replaces build_analytical_model + chi_squared, apf_step2.py:78-137):
+//                   row table + column table -> factorised loop (row_steps_fast: one exponential
+//                   per 4-pixel group and component) or plain loop (row_steps: one per pixel)
+//   tmem_*          tensor memory as a per-lane pixel store (tcgen05.alloc / st / ld)
 //   philox / draws  counter-based random stream (replaces numpy's global MT, apf_step2.py:64,68,143,302)
 //
 // Numerics: pixel terms in FP32 with stamp-local coordinates, ex2.approx
