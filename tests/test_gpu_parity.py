@@ -670,3 +670,49 @@ def test_batched_sampler_partitions(gpu):
     assert bool((tries.sum(dim=1) == 3).all())
     for w in (0, 511, 512, 607, 608, 44444, W - 38, W - 1):
         assert torch.equal(chain[:, w], solo(int(frame_of[w]), w, init[w], 3, 5)), "walker %d" % w
+
+
+def test_stream_of_epochs_reuses_domain_and_sampler(gpu):
+    """A service processing batch after batch (bench.py's e2e): new frames and origins go into the
+    SAME device buffers (prepare_domain(into=...)), the sampler is reset, chain rows leave through
+    the double-buffered ChainStreamer.  Every batch must equal a fresh domain + fresh sampler."""
+    torch, synth, frame, sampler = gpu["torch"], gpu["synth"], gpu["frame"], gpu["sampler"]
+    size, nf, walkers, n_upd = 64, 3, 40, 48
+    frame_of = (np.arange(walkers) % nf).astype(np.int32)
+    batches = []
+    for b in range(3):
+        stamps, origins = synth.make_stamps(nf, size, 2)
+        stamps = stamps[::-1].copy() if b == 1 else stamps + np.float32(b)        # different pixels ...
+        origins = origins[::-1].copy() if b == 1 else origins + b                # ... and different origins
+        p = []
+        for f in range(nf):
+            g = synth.step1_guess(stamps[f], 2, origin=tuple(origins[f]))
+            p.append(frame.initial_parameters(stamps[f], g, 2, origin=tuple(origins[f])))
+        batches.append((stamps, origins, np.asarray(p)[frame_of]))
+
+    fresh = []
+    for b, (stamps, origins, init) in enumerate(batches):
+        dom = frame.prepare_domain(stamps, HEADER, origin=origins, nbody=2)
+        with sampler.GibbsSampler(dom, init, frame_of, seed=50 + b, thin=4) as s:
+            fresh.append((s.run(n_upd).cpu().numpy(), [t.cpu().numpy() for t in s.state()]))
+
+    stamps, origins, init = batches[0]
+    dom = frame.prepare_domain(stamps, HEADER, origin=origins, nbody=2)
+    got = []
+    with sampler.GibbsSampler(dom, init, frame_of, seed=50, thin=4) as s:
+        streamer = sampler.ChainStreamer(s, n_upd)
+        for b, (stamps, origins, init) in enumerate(batches):
+            if b > 0:
+                frame.prepare_domain(torch.from_numpy(stamps).to(dom.device), HEADER, origin=origins, nbody=2, into=dom)
+                s.reset(init, seed=50 + b)
+            prev = streamer.run(n_upd)
+            if prev is not None:
+                got.append(prev.copy())
+            if b == len(batches) - 1:
+                state = [t.cpu().numpy() for t in s.state()]
+        got.append(streamer.finish().copy())
+    assert len(got) == 3
+    for b in range(3):
+        assert np.array_equal(got[b], fresh[b][0]), "batch %d" % b
+    for x, y in zip(state, fresh[2][1]):
+        assert np.array_equal(x, y)
