@@ -135,7 +135,7 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
     cf.floor = tf[warp][pr.floor_index];
     load_shape<NB>(cf, 0, tf[warp]);
     load_shape<NB>(cf, 1, tf[warp]);
-    __shared__ __align__(16) float rt[4][Scratch<NB, NY>::FLOATS];
+    __shared__ __align__(16) float rt[4][Scratch<NB, NX, NY>::FLOATS];
     set_fast<NB, NX, NY>(cf, lane);
     if (pr.plain) cf.fast = false;
     if (NX >= 64 && pr.cull) set_cull<NB, NX, NY>(cf, lane); else no_cull<NB, NX, NY>(cf);
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
         }
         const int team = warp / TEAM, tw = warp % TEAM;
         if (team < a.item_count[it])
-            run_walker<NB, NX, NY, TEAM>(a, sd, sw, scratch[warp], rt + warp * Scratch<NB, NY, TEAM>::FLOATS, team_part[team],
+            run_walker<NB, NX, NY, TEAM>(a, sd, sw, scratch[warp], rt + warp * Scratch<NB, NX, NY, TEAM>::FLOATS, team_part[team],
                                          team, tw, a.walker_of[a.item_first[it] + team], f, lane);
     }
 }
@@ -571,7 +571,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
 template <int NB, int NX, int NY, int NW, int LW>
 __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_constant__ RunArgs a) {
     using I = CoefImg<NB, Geo<NX>::PANELS>;
-    constexpr int TAB = Scratch<NB, NY>::FLOATS;
+    constexpr int TAB = Scratch<NB, NX, NY>::FLOATS;
     // stamps of up to 64 x 64 pixels also live in the TMEM pixel store (see tmem_fill_stamp)
     // (128 x 128: the weight plane only, the data plane is read from shared memory)
     constexpr int TM = (Geo<NX>::PANELS == 1 && Rows<NY, 1>::HALVES == 1) ? 1 : 2;
@@ -972,7 +972,7 @@ static int configure_gibbs(lapf_sampler* s) {
     auto kern = gibbs_kernel<NB, NX, NX, NW, MINB, TEAM>;
     s->nw = NW / TEAM;   // walkers per CTA item
     s->minb = MINB;
-    constexpr size_t kBytes = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * Scratch<NB, NX, TEAM>::FLOATS;
+    constexpr size_t kBytes = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * Scratch<NB, NX, NX, TEAM>::FLOATS;
     static_assert(kBytes + 16 * 1024 <= 227 * 1024, "team kernel: shared memory per CTA (dynamic + static scratch)");
     s->smem = kBytes;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
@@ -998,7 +998,7 @@ static int configure_batch(lapf_sampler* s) {
     s->nw = NW;
     s->chunk = NW * LW;
     s->minb = 1;
-    constexpr size_t kBytes = sizeof(float) * (2 * NX * NX + NW * Scratch<NB, NX>::FLOATS + NW * LW * CoefImg<NB, Geo<NX>::PANELS>::STRIDE);
+    constexpr size_t kBytes = sizeof(float) * (2 * NX * NX + NW * Scratch<NB, NX, NX>::FLOATS + NW * LW * CoefImg<NB, Geo<NX>::PANELS>::STRIDE);
     static_assert(kBytes + 256 <= 227 * 1024, "batched kernel: shared memory per CTA");
     s->smem = kBytes;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
@@ -1024,10 +1024,10 @@ static int launch_batch(lapf_sampler* s, const RunArgs& a, cudaStream_t st) {
         const int nb__ = s->cfg.problem.nbody, nx__ = s->cfg.problem.nx;                    \
         if (nb__ == 2 && nx__ == 32) return FN<2, 32, 16, 32>(__VA_ARGS__);                 \
         if (nb__ == 2 && nx__ == 64) return FN<2, 64, 16, 32>(__VA_ARGS__);                 \
-        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 16, 15>(__VA_ARGS__);               \
+        if (nb__ == 2 && nx__ == 128) return FN<2, 128, 12, 16>(__VA_ARGS__);               \
         if (nb__ == 3 && nx__ == 32) return FN<3, 32, 16, 32>(__VA_ARGS__);                 \
-        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 16, 28>(__VA_ARGS__);                 \
-        if (nb__ == 3 && nx__ == 128) return FN<3, 128, 12, 16>(__VA_ARGS__);               \
+        if (nb__ == 3 && nx__ == 64) return FN<3, 64, 16, 32>(__VA_ARGS__);                 \
+        if (nb__ == 3 && nx__ == 128) return FN<3, 128, 12, 12>(__VA_ARGS__);               \
         return fail(LAPF_ERR_INVALID, "unsupported sampler shape nbody=%d nx=%d", nb__, nx__); \
     } while (0)
 

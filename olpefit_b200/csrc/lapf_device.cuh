@@ -332,132 +332,97 @@ __device__ __forceinline__ void coef_from_vector(Coef<NB>& cf, const double (&v)
 // ---------------------------------------------------------------------------------------------
 // The pixel loop: one warp evaluates chi-square of one parameter vector over an NY x NX stamp.
 //
-// Lane geometry.  Columns are processed in panels of PW = min(NX, 64).  Inside a panel a lane
-// owns 8 fixed columns (two groups of 4 for 128-bit loads) and every RG-th row, so
-//   * the column offsets dx[k][j] = x_j - x0_k live in registers for the whole panel
-//     (no per-pixel subtract),
-//   * the row-dependent terms  sb*dy, sc*dy^2  are computed once per row and shared by 8 pixels,
-//   * per pixel and component the work is 2 FFMA + 1 MUFU.EX2 + 1 FFMA.
-// Each quarter-warp reads 128 contiguous bytes per LDS.128: conflict-free for NX = 64/128; for
-// NX = 32 odd row groups take their two column groups in swapped order, which keeps the two rows
-// a quarter-warp touches on disjoint banks.
+// Lane geometry.  Columns are processed in panels of PW = min(NX, 64).  A WARP STEP covers RG rows
+// of a panel (4 rows x 64 columns, or 8 rows x 32 columns): lane (b, a) owns the 2 x 4 pixel BLOCK
+// of rows 2b, 2b+1 of the step and columns 4a .. 4a+3 of the panel -- 8 pixels, two 128-bit loads
+// per plane (16 lanes read 256 contiguous bytes of a row: conflict-free).  The column offsets of a
+// lane never change, so everything that depends on them lives in registers for the whole panel.
 // ---------------------------------------------------------------------------------------------
 template <int NX>
 struct Geo {
     static constexpr int PW = NX >= 64 ? 64 : 32;
     static constexpr int PANELS = NX / PW;
-    static constexpr int LPR = PW / 8;        // lanes per row
-    static constexpr int RG = 32 / LPR;       // rows handled by a warp per step
+    static constexpr int GPR = PW / 4;        // 4-pixel column groups across a panel: 16 / 8
+    static constexpr int BPS = 32 / GPR;      // 2-row blocks per warp step: 2 / 4
+    static constexpr int RG = 2 * BPS;        // rows per warp step: 4 / 8
     static_assert(NX % PW == 0 && (NX == 32 || NX % 64 == 0), "unsupported stamp width");
 };
 
-// Row table: everything that depends on the row only, computed ONCE per proposal by the warp
-// (one or two rows per lane) instead of once per row step by every lane.  One entry of Tab::RS
-// floats per row r:
-//   [2k], [2k+1]          sb_k * dy_k,  sc_k * dy_k^2     (dy_k = r - y0_k), for component k < K
-//   [2K + 4c .. +3]       2^(j h)  for j = -3, -1, 1, 3,  h  = sb_c (r - y0_c) / 2,   shape class c
-//   [2K + 8 + 4c .. +3]   2^(j h') for j = -3, -1, 1, 3,  h' = h + sa_c * D
-// The first pair gives the exponent of component k at any column of the row:
-//   q = fma(dx, fma(sa, dx, sb*dy), sc*dy^2);
-// the second the factors that move it half a pixel / one and a half pixels left or right of the
-// anchor column of a lane's column group A, the third the same for its group B, whose anchor is
-// D = +-PW/2 columns away (see row_steps_fast; the sign follows the row for 32-pixel panels, where
-// odd rows take their groups in swapped order).  y0_c is the centre of the class's FIRST component;
-// the other components of the class fold their offset into the lane constants.
-// The entry is padded to 28 floats so the 4 (or 8) row groups of a warp read distinct banks.
+// Block table: everything that depends on the rows only, computed ONCE per proposal by the warp
+// (one 2-row block per lane) instead of once per step by every lane.  One entry of Tab::RS floats
+// per block, with yb the centre of its two rows and dyb_k = yb - y0_k:
+//   [2k], [2k+1]              sb_k * dyb_k,  sc_k * dyb_k^2        for component k < K
+//   [2K + 8c .. 2K + 8c + 7]  T_c,ij = 2^(j (sb dyb_c + i sb) + 2 i sc dyb_c + sc / 4)   shape class c,
+//                             i = -1/2 then +1/2 (row), j = -3/2, -1/2, 1/2, 3/2 (column)
+// The first pair gives the exponent of component k at the centre of a lane's block,
+//   q0 = fma(dxa, fma(sa, dxa, sb*dyb), sc*dyb^2),        dxa = anchor column - x0_k;
+// T moves it to the 8 pixels of the block (see row_steps_fast).  y0_c is the centre of the class's
+// FIRST component; the other components of the class fold their offset into the lane constants.
+// The entry is padded to 28 floats so the blocks of a warp step read distinct banks.
 template <int NB>
 struct Tab {
     static constexpr int K = 2 * NB;
     static constexpr int RS = 28;
-    static constexpr int OFF_RA = 2 * K;
-    static constexpr int OFF_RB = 2 * K + 8;
-    static_assert(OFF_RB + 8 <= RS && OFF_RA % 4 == 0, "row table entry layout");
+    static constexpr int OFF_T = 2 * K;
+    static_assert(OFF_T + 16 <= RS && OFF_T % 4 == 0, "block table entry layout");
 };
 
 // A table covers TR rows of the stamp; taller stamps are walked table by table ("half").  A team
-// member (TEAM warps share one walker, warp tw takes every TEAM-th row step) only builds the
-// TR / TEAM rows it evaluates.
+// member (TEAM warps share one walker, warp tw takes every TEAM-th warp step) only builds the
+// blocks of the steps it evaluates.
 template <int NY, int TEAM = 1>
 struct Rows {
-    static constexpr int TR = (NY >= 128 && TEAM == 1) ? 32 : (NY < 64 ? NY : 64);   // rows per table
+    static constexpr int TR = NY < 64 ? NY : 64;       // rows per table
     static constexpr int HALVES = NY / TR;
-    static constexpr int NR = TR / TEAM;                                             // rows a warp builds
-    static_assert(NY % TR == 0 && TR % TEAM == 0, "unsupported stamp height");
+    static constexpr int NBLK = TR / 2 / TEAM;         // blocks a warp builds
+    static_assert(NY % TR == 0 && (TR / 2) % TEAM == 0, "unsupported stamp height");
 };
 
-// per-warp shared-memory scratch of the pixel loop: the row table, then the column table
-// (coop_consts: [component][group-A anchor 0..7][4 pixel offsets])
-template <int NB, int NY, int TEAM = 1>
+// per-warp shared-memory scratch of the pixel loop: the block table, then the column table
+// (coop_consts: [component][row of the block][anchor][4 column offsets])
+template <int NB, int NX, int NY, int TEAM = 1>
 struct Scratch {
-    static constexpr int TAB = Rows<NY, TEAM>::NR * Tab<NB>::RS;
-    static constexpr int CT = 2 * NB * 8 * 4;
+    static constexpr int TAB = Rows<NY, TEAM>::NBLK * Tab<NB>::RS;
+    static constexpr int CT = 2 * NB * 2 * Geo<NX>::GPR * 4;
     static constexpr int FLOATS = TAB + CT;
 };
 
 template <int NB, int NX, int TR, int TEAM>
 __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Coef<NB>& cf, int lane, int row0, int tw) {
-    constexpr int K = 2 * NB;
-    constexpr int NR = TR / TEAM;
-    constexpr int RG = Geo<NX>::RG;
-    constexpr float HALF = 0.5f * Geo<NX>::PW;
+    using G = Geo<NX>;
     using T = Tab<NB>;
+    constexpr int K = 2 * NB;
+    constexpr int NBLK = TR / 2 / TEAM;
     __syncwarp();   // readers of the previous table are done
-    if (NR == 64) {
-        // two rows (r, r+32) per pass, as the two halves of packed FP32 operations (TEAM = 1 here)
-        const float2 fr = make_float2((float)(row0 + lane), (float)(row0 + 32 + lane));
-        float4* o0 = reinterpret_cast<float4*>(rt + lane * T::RS);
-        float4* o1 = reinterpret_cast<float4*>(rt + (32 + lane) * T::RS);
-        float2 v[2 * K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float2 yd = __fadd2_rn(fr, make_float2(-cf.y0[k], -cf.y0[k]));
-            const float2 sc2 = make_float2(cf.sc[k & 1], cf.sc[k & 1]);
-            v[2 * k] = __fmul2_rn(make_float2(cf.sb[k & 1], cf.sb[k & 1]), yd);
-            v[2 * k + 1] = __fmul2_rn(__fmul2_rn(sc2, yd), yd);
-        }
+    for (int j0 = 0; j0 < NBLK; j0 += 32) {
+        const int jb = j0 + lane;                  // local block: warp step jb / BPS of this warp, block jb % BPS
+        if (NBLK % 32 == 0 || jb < NBLK) {
+            const int step = (jb / G::BPS) * TEAM + tw;
+            const float yb = (float)(row0 + step * G::RG + 2 * (jb % G::BPS)) + 0.5f;
+            float4* o = reinterpret_cast<float4*>(rt + jb * T::RS);
+            float v[2 * K];
 #pragma unroll
-        for (int q = 0; q < 2 * K / 4; ++q) {
-            o0[q] = make_float4(v[4 * q].x, v[4 * q + 1].x, v[4 * q + 2].x, v[4 * q + 3].x);
-            o1[q] = make_float4(v[4 * q].y, v[4 * q + 1].y, v[4 * q + 2].y, v[4 * q + 3].y);
-        }
-        // 64-row tables belong to 64-pixel panels: group B is always +PW/2 away (no swapped rows)
+            for (int k = 0; k < K; ++k) {
+                const float yd = yb - cf.y0[k];
+                v[2 * k] = cf.sb[k & 1] * yd;
+                v[2 * k + 1] = (cf.sc[k & 1] * yd) * yd;
+            }
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const float2 h = __fmul2_rn(v[2 * c], make_float2(0.5f, 0.5f));     // sb_c * dy_c / 2
-            const float2 h3 = __fmul2_rn(v[2 * c], make_float2(1.5f, 1.5f));
-            o0[T::OFF_RA / 4 + c] = make_float4(ex2_approx(-h3.x), ex2_approx(-h.x), ex2_approx(h.x), ex2_approx(h3.x));
-            o1[T::OFF_RA / 4 + c] = make_float4(ex2_approx(-h3.y), ex2_approx(-h.y), ex2_approx(h.y), ex2_approx(h3.y));
-            const float sd = cf.sa[c] * HALF;
-            const float2 g = __fadd2_rn(h, make_float2(sd, sd));
-            const float2 g3 = __fmul2_rn(g, make_float2(3.f, 3.f));
-            o0[T::OFF_RB / 4 + c] = make_float4(ex2_approx(-g3.x), ex2_approx(-g.x), ex2_approx(g.x), ex2_approx(g3.x));
-            o1[T::OFF_RB / 4 + c] = make_float4(ex2_approx(-g3.y), ex2_approx(-g.y), ex2_approx(g.y), ex2_approx(g3.y));
-        }
-    } else {
+            for (int q = 0; q < 2 * K / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            const float2 jlo = make_float2(-1.5f, -0.5f), jhi = make_float2(0.5f, 1.5f);
 #pragma unroll
-        for (int j0 = 0; j0 < NR; j0 += 32) {
-            const int j = j0 + lane;                    // local row: row step j / RG of this warp, row group j % RG
-            if (NR % 32 == 0 || j < NR) {
-                const int r = row0 + ((j / RG) * TEAM + tw) * RG + (j % RG);
-                const float fr = (float)r;
-                float4* o = reinterpret_cast<float4*>(rt + j * T::RS);
-                float v[2 * K];
+            for (int c = 0; c < 2; ++c) {
+                const float p = v[2 * c];                       // sb_c * dyb_c (component c is the class's first)
+                const float s = (cf.sc[c] * (yb - cf.y0[c])) * 2.f;
+                const float g = 0.25f * cf.sc[c];
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float yd = fr - cf.y0[k];
-                    v[2 * k] = cf.sb[k & 1] * yd;
-                    v[2 * k + 1] = (cf.sc[k & 1] * yd) * yd;
-                }
-#pragma unroll
-                for (int q = 0; q < 2 * K / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                // odd rows of a 32-pixel panel take their column groups in swapped order
-                const float dlt = (Geo<NX>::PW == 32 && (r & 1)) ? -HALF : HALF;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float h = v[2 * c] * 0.5f, h3 = v[2 * c] * 1.5f;
-                    o[T::OFF_RA / 4 + c] = make_float4(ex2_approx(-h3), ex2_approx(-h), ex2_approx(h), ex2_approx(h3));
-                    const float g = h + cf.sa[c] * dlt, g3 = g * 3.f;
-                    o[T::OFF_RB / 4 + c] = make_float4(ex2_approx(-g3), ex2_approx(-g), ex2_approx(g), ex2_approx(g3));
+                for (int ii = 0; ii < 2; ++ii) {
+                    const float i = ii ? 0.5f : -0.5f;
+                    const float pj = fmaf(i, cf.sb[c], p), base = fmaf(i, s, g);
+                    const float2 pj2 = make_float2(pj, pj), b2 = make_float2(base, base);
+                    const float2 alo = __ffma2_rn(jlo, pj2, b2), ahi = __ffma2_rn(jhi, pj2, b2);
+                    o[T::OFF_T / 4 + 2 * c + ii] = make_float4(ex2_approx(alo.x), ex2_approx(alo.y), ex2_approx(ahi.x), ex2_approx(ahi.y));
                 }
             }
         }
@@ -593,19 +558,22 @@ __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
 }
 
 // The factorised pixel loop multiplies factors whose exponents can be large although their sum is
-// not.  It is used only when, for every pixel of the stamp, the column factor's exponent
-// |j (sa (2 dxa + j) + w_k)| and the row factor's |1.5 (sb dy + sa PW)| stay below 40 -- no factor overflows
-// or underflows on its own -- and when an anchor exponential that underflows (q0 < -126) implies
-// that its four pixels are below 2^-46 |A| <= 2^-25 |floor|.  Anything else, nan and inf included,
-// takes the plain loop (one exponential per pixel and component).  The decision is a function of
-// the coefficients only and is the same in every lane.
+// not.  It is used only when, for every pixel of the stamp, the lane constants' exponent
+// |j (sa (2 dxa + j) + sb dy0) + i (sb dxa + 2 sc dy0)| and the block factors' exponent
+// |j sb (dyb + i) + 2 i sc dyb + sc / 4| stay below 40 -- no factor overflows or underflows on its
+// own -- and when an anchor exponential that underflows (q0 < -126) implies that its eight pixels
+// are below 2^-46 |A| <= 2^-25 |floor|.  Anything else, nan and inf included, takes the plain loop
+// (one exponential per pixel and component).  The decision is a function of the coefficients only
+// and is the same in every lane.
 template <int NX, int NY>
 __device__ __forceinline__ bool fast_one(float a, float x0, float y0, float yref, float sa, float sb, float sc,
                                          float floor_v) {
     const float dxm = fabsf(x0 - 0.5f * NX) + 0.5f * NX;      // >= |anchor - x0| for every anchor column
-    const float argc = 1.5f * (fabsf(sa) * (2.f * dxm + 1.5f) + fabsf(sb * (yref - y0)));
-    const float argr = 1.5f * (fabsf(sb) * (fabsf(yref - 0.5f * NY) + 0.5f * NY) + fabsf(sa) * Geo<NX>::PW);
-    return argc <= 40.f && argr <= 40.f && fabsf(sc) <= 1e30f &&
+    const float dym = fabsf(yref - 0.5f * NY) + 0.5f * NY;    // >= |block centre - y0_c| for every block
+    const float dy0 = fabsf(yref - y0);
+    const float argc = 1.5f * (fabsf(sa) * (2.f * dxm + 1.5f) + fabsf(sb) * dy0) + 0.5f * (fabsf(sb) * dxm + 2.f * fabsf(sc) * dy0);
+    const float argt = 1.5f * fabsf(sb) * (dym + 0.5f) + fabsf(sc) * (dym + 0.25f);
+    return argc <= 40.f && argt <= 40.f && fabsf(sc) <= 1e30f &&
            fabsf(a) <= 0x1p21f * fabsf(floor_v) && fabsf(a) <= 1e12f;    // all false on nan
 }
 
@@ -633,33 +601,34 @@ __device__ __forceinline__ void set_fast_serial(Coef<NB>& cf) {
     cf.fast = ok;
 }
 
-// Row steps [i0, i1) of one panel for the component classes KIND says (0: none, the model is the
+// Warp steps [i0, i1) of one panel for the component classes KIND says (0: none, the model is the
 // floor; 1: wide wings only; 2: all components).  chi-square terms are added to the four FP32
-// accumulators s0, s1 in row order, whatever the segmentation (so culling does not regroup sums).
+// accumulators s0, s1 in step order, whatever the segmentation (so culling does not regroup sums).
 // PREP = true: the planes hold d*sqrt(w) and -sqrt(w) (the sampler converts a stamp once after
 // staging it); PREP = false: raw data / weight planes, converted per pixel.  Both give
 // bit-identical chi-square: the residual is always  r = fma(-sqrt(w), m, d*sqrt(w)),  chi2 += r*r.
-struct StepPtrs {          // where the next row step of this lane lives
-    const float* rp;       // row table
-    const float* dp;       // data plane
-    const float* wp;       // weight plane
-    float* mp;             // model output (STORE only)
-    uint32_t tm;           // TMEM address of the lane's 16 values (TM only)
+struct StepPtrs {          // where the next warp step of this lane lives
+    const float* rp;       // block table entry
+    const float* dp;       // data plane, first row of the block at the lane's columns
+    const float* wp;       // weight plane, same
+    float* mp;             // model output (STORE only), same
+    uint32_t tm;           // TMEM address of the lane's values (TM only)
+    float row;             // first row of the block (plain loop only)
 };
 
-// model of 8 pixels -> (optional store) -> residuals -> chi-square accumulators
+// model of 8 pixels (pairs: row 0 px 0-1, row 0 px 2-3, row 1 px 0-1, row 1 px 2-3) -> (optional
+// store) -> residuals -> chi-square accumulators
 template <int NX, bool STORE, bool PREP>
-__device__ __forceinline__ void finish_step(const float2 (&m)[4], const float4& dA, const float4& dB,
-                                            const float4& wA, const float4& wB, float* mp, int colA, int colB,
-                                            float2& s0, float2& s1) {
+__device__ __forceinline__ void finish_step(const float2 (&m)[4], const float4& d0, const float4& d1,
+                                            const float4& w0, const float4& w1, float* mp, float2& s0, float2& s1) {
     if (STORE) {
-        *reinterpret_cast<float4*>(mp + colA) = make_float4(m[0].x, m[0].y, m[1].x, m[1].y);
-        *reinterpret_cast<float4*>(mp + colB) = make_float4(m[2].x, m[2].y, m[3].x, m[3].y);
+        *reinterpret_cast<float4*>(mp) = make_float4(m[0].x, m[0].y, m[1].x, m[1].y);
+        *reinterpret_cast<float4*>(mp + NX) = make_float4(m[2].x, m[2].y, m[3].x, m[3].y);
     }
-    float2 dv[4] = {make_float2(dA.x, dA.y), make_float2(dA.z, dA.w), make_float2(dB.x, dB.y),
-                    make_float2(dB.z, dB.w)};
-    float2 wv[4] = {make_float2(wA.x, wA.y), make_float2(wA.z, wA.w), make_float2(wB.x, wB.y),
-                    make_float2(wB.z, wB.w)};
+    float2 dv[4] = {make_float2(d0.x, d0.y), make_float2(d0.z, d0.w), make_float2(d1.x, d1.y),
+                    make_float2(d1.z, d1.w)};
+    float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                    make_float2(w1.z, w1.w)};
     if (!PREP) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -678,128 +647,131 @@ __device__ __forceinline__ void finish_step(const float2 (&m)[4], const float4& 
 }
 
 // ---- plain loop: one exponential per pixel and component -------------------------------------
-// Arithmetic is issued as packed FFMA2 (fma.rn.f32x2, new on sm_100): two adjacent pixels per
-// instruction, scalar coefficients as broadcast operands.  Per pixel PAIR and component that is
-// 3 FFMA2 + 2 MUFU.EX2: SFU-bound.  Kept for parameter vectors set_fast turns away.
-template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND>
-__device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)[2 * NB][4], float2& s0, float2& s1,
-                                          int& i, int i1, StepPtrs& sp, int colA, int colB) {
+// q = fma(dx, fma(sa, dx, sb*dy), sc*dy^2), e = ex2(q), m = fma(A, e, m) per pixel and component,
+// issued as packed FFMA2 (fma.rn.f32x2, new on sm_100: two adjacent pixels per instruction, scalar
+// coefficients as broadcast operands) -- 3 FFMA2 + 2 MUFU.EX2 per pixel PAIR and component:
+// SFU-bound.  Kept for parameter vectors set_fast turns away; it takes no table (the row terms are
+// worked out per row on the spot).
+template <int NB, int NX, int NY, bool STORE, bool PREP>
+__device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)[2 * NB][2], float2& s0, float2& s1,
+                                          int& i, int i1, StepPtrs& sp) {
     using G = Geo<NX>;
-    using T = Tab<NB>;
     constexpr int K = 2 * NB;
-    const float* rp = sp.rp;
     const float* dp = sp.dp;
     const float* wp = sp.wp;
     float* mp = sp.mp;
+    float row = sp.row;
 #pragma unroll 1
     for (; i < i1; ++i) {
-        const float4 dA = *reinterpret_cast<const float4*>(dp + colA);
-        const float4 dB = *reinterpret_cast<const float4*>(dp + colB);
-        const float4 wA = *reinterpret_cast<const float4*>(wp + colA);
-        const float4 wB = *reinterpret_cast<const float4*>(wp + colB);
+        const float4 d0 = *reinterpret_cast<const float4*>(dp);
+        const float4 d1 = *reinterpret_cast<const float4*>(dp + NX);
+        const float4 w0 = *reinterpret_cast<const float4*>(wp);
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + NX);
         float2 m[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) m[j] = make_float2(cf.floor, cf.floor);
-        if (KIND > 0) {
-            float rc[2 * K];
 #pragma unroll
-            for (int q = 0; q < 2 * K / 4; ++q) {
-                const float4 t4 = reinterpret_cast<const float4*>(rp)[q];
-                rc[4 * q] = t4.x; rc[4 * q + 1] = t4.y; rc[4 * q + 2] = t4.z; rc[4 * q + 3] = t4.w;
-            }
+        for (int k = 0; k < K; ++k) {
+            const float2 sa2 = make_float2(cf.sa[k & 1], cf.sa[k & 1]);
+            const float2 am2 = make_float2(cf.amp[k], cf.amp[k]);
 #pragma unroll
-            for (int k = (KIND == 2 ? 0 : 1); k < K; k += (KIND == 2 ? 1 : 2)) {
-                const float2 sa2 = make_float2(cf.sa[k & 1], cf.sa[k & 1]);
-                const float2 by2 = make_float2(rc[2 * k], rc[2 * k]);
-                const float2 cy2 = make_float2(rc[2 * k + 1], rc[2 * k + 1]);
-                const float2 am2 = make_float2(cf.amp[k], cf.amp[k]);
+            for (int r = 0; r < 2; ++r) {
+                const float yd = (row + (float)r) - cf.y0[k];
+                const float by = cf.sb[k & 1] * yd, cy = (cf.sc[k & 1] * yd) * yd;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 t = __ffma2_rn(sa2, xd[k][j], by2);
-                    const float2 q = __ffma2_rn(xd[k][j], t, cy2);
+                for (int j = 0; j < 2; ++j) {
+                    const float2 t = __ffma2_rn(sa2, xd[k][j], make_float2(by, by));
+                    const float2 q = __ffma2_rn(xd[k][j], t, make_float2(cy, cy));
                     const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
-                    m[j] = __ffma2_rn(am2, e, m[j]);
+                    m[2 * r + j] = __ffma2_rn(am2, e, m[2 * r + j]);
                 }
             }
         }
-        finish_step<NX, STORE, PREP>(m, dA, dB, wA, wB, mp, colA, colB, s0, s1);
+        finish_step<NX, STORE, PREP>(m, d0, d1, w0, w1, mp, s0, s1);
         if (STORE) mp += G::RG * NX;
-        rp += G::RG * T::RS;
         dp += G::RG * NX;
         wp += G::RG * NX;
+        row += (float)G::RG;
     }
-    sp.rp = rp; sp.dp = dp; sp.wp = wp; sp.mp = mp;
+    sp.dp = dp; sp.wp = wp; sp.mp = mp; sp.row = row;
 }
 
 // ---- factorised loop -------------------------------------------------------------------------
-// A lane's 8 columns are two groups of 4 adjacent pixels.  With the anchor xa at the centre of a
-// group (between its 2nd and 3rd pixel) and j in {-1.5, -0.5, 0.5, 1.5},
-//     q_k(xa + j, r) = q_k(xa, r) + j (sa (2 dxa_k + j)) + j sb dy_k,        dxa_k = xa - x0_k,
-// and dy_k = (r - y0_c) + (y0_c - y0_k) with c the first component of k's shape class, so
-//     A_k 2^q_k(xa + j, r) = E_k(r) * C_kj * R_cj(r)
-//     E_k(r)  = 2^q_k(xa, r)                         one MUFU.EX2 per GROUP and component
-//     C_kj    = A_k 2^(j (sa (2 dxa_k + j) + sb (y0_c - y0_k)))    lane constant (registers)
-//     R_cj(r) = 2^(j sb (r - y0_c))                  row table, shared by the class
-// and a class adds  R_cj * sum_k C_kj E_k  to the pixel: per pixel pair NB + 1 packed operations
-// for NB components, plus 2 FFMA2 + 2 MUFU per component for the two anchors.  The anchor of
-// group B is D = +-PW/2 columns from group A's, so C_kj(B) = C_kj(A) 2^(2 j sa D): the lane keeps
-// the constants of group A only and group B takes its factor from a second row-table entry
-// R'_cj = R_cj 2^(2 j sa D).  A row step of 8 pixels x 4 components is 40 packed FP32
-// instructions and 8 MUFU (plain loop: 56 and 32): the loop is bound by the FP32 pipe, not the SFU.
+// The exponent is a quadratic form, so around the centre (xa, yb) of a lane's 2 x 4 block, with
+// i in {-1/2, 1/2} (row), j in {-3/2, -1/2, 1/2, 3/2} (column), dxa_k = xa - x0_k, dyb_k = yb - y0_k,
+//     q_k(xa + j, yb + i) = q_k(xa, yb) + j sa (2 dxa_k + j) + sb (i dxa_k + j dyb_k + i j)
+//                                        + i sc (2 dyb_k + i),
+// and dyb_k = dyb_c + (y0_c - y0_k) with c the first component of k's shape class, so
+//     A_k 2^q_k(xa + j, yb + i) = E_k * C_k,ij * T_c,ij
+//     E_k    = 2^q_k(xa, yb)                            ONE MUFU.EX2 per block and component
+//     C_k,ij = A_k 2^(j (sa (2 dxa_k + j) + sb dy0_k) + i (sb dxa_k + 2 sc dy0_k))   lane constant (registers),
+//                                                       dy0_k = y0_c - y0_k
+//     T_c,ij = 2^(j sb (dyb_c + i) + 2 i sc dyb_c + sc / 4)                          block table, shared by the class
+// and a class adds  T_c,ij * sum_k C_k,ij E_k  to the pixel: per pixel pair NB + 1 packed
+// operations for NB components, plus 2 FFMA + 1 MUFU per component for the anchor.  A warp step
+// of 8 pixels x 4 components is 32 packed + 8 scalar FP32 instructions and 4 MUFU (plain loop: 56
+// packed and 32 MUFU): the loop is bound by FP32 issue, not by the SFU.
 template <int NB>
 struct LaneK {
     static constexpr int K = 2 * NB;
-    float2 dxa[K];       // (group A, group B) anchor offset to the centre of component k
-    float2 C[K][2];      // group A, pixel pairs (-1.5,-0.5) and (0.5,1.5)
+    float dxa[K];        // anchor offset to the centre of component k
+    float2 C[K][4];      // pixel pairs: row 0 (-3/2,-1/2), row 0 (1/2,3/2), row 1 (-3/2,-1/2), row 1 (1/2,3/2)
 };
 
-// The C_kj of the 8 group-A anchors of a panel (columns 4a + 1.5, a = 0..7), worked out once per
-// proposal by the warp -- lane (a, k) does component k at anchor a -- and handed round through the
-// column table ct[k][a][4]; every lane then reads the 4K values of its own anchor.
+// The C_k,ij of the GPR anchors of a panel (columns 4a + 1.5), worked out once per proposal by the
+// warp -- one (anchor, component) pair per lane and round -- and handed round through the column
+// table ct[k][row of the block][a][4]; every lane then reads the 8K values of its own anchor.
 template <int NB, int NX>
-__device__ __forceinline__ void coop_consts(LaneK<NB>& lk, float* __restrict__ ct, const Coef<NB>& cf, int lane,
-                                            int pan, int colA, int colB) {
+__device__ __forceinline__ void coop_consts(LaneK<NB>& lk, float* __restrict__ ct, const Coef<NB>& cf, int lane, int pan) {
     using G = Geo<NX>;
     constexpr int K = 2 * NB;
     __syncwarp();   // readers of the previous column table are done
-    const int a = lane & 7;
-    const float xa = (float)(pan * G::PW + 4 * a) + 1.5f;
 #pragma unroll
-    for (int kk0 = 0; kk0 < K; kk0 += 4) {
-        const int kk = kk0 + (lane >> 3);
-        if (K % 4 == 0 || kk < K) {
+    for (int t0 = 0; t0 < G::GPR * K; t0 += 32) {
+        const int t = t0 + lane;
+        if ((G::GPR * K) % 32 == 0 || t < G::GPR * K) {
+            const int a = t % G::GPR, kk = t / G::GPR;
             float amp = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
 #pragma unroll
             for (int k = 1; k < K; ++k)
                 if (kk == k) { amp = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
             const int c = kk & 1;
-            const float sa = c ? cf.sa[1] : cf.sa[0], sb = c ? cf.sb[1] : cf.sb[0];
-            const float wk = sb * ((c ? cf.y0[1] : cf.y0[0]) - y0);      // exactly 0 for the class's first component
-            const float d2 = 2.f * (xa - x0);
-            const float2 w2 = make_float2(wk, wk), sa2 = make_float2(sa, sa), am = make_float2(amp, amp);
+            const float sa = c ? cf.sa[1] : cf.sa[0], sb = c ? cf.sb[1] : cf.sb[0], sc = c ? cf.sc[1] : cf.sc[0];
+            const float dy0 = (c ? cf.y0[1] : cf.y0[0]) - y0;           // exactly 0 for the class's first component
+            const float dxa = ((float)(pan * G::PW + 4 * a) + 1.5f) - x0;
+            const float u = sb * dy0, d2 = 2.f * dxa;
+            const float v = fmaf(sb, dxa, 2.f * (sc * dy0));
+            const float2 u2 = make_float2(u, u), sa2 = make_float2(sa, sa), d22 = make_float2(d2, d2);
             const float2 jlo = make_float2(-1.5f, -0.5f), jhi = make_float2(0.5f, 1.5f);
-            const float2 alo = __fmul2_rn(jlo, __ffma2_rn(sa2, __fadd2_rn(make_float2(d2, d2), jlo), w2));
-            const float2 ahi = __fmul2_rn(jhi, __ffma2_rn(sa2, __fadd2_rn(make_float2(d2, d2), jhi), w2));
-            const float2 clo = __fmul2_rn(am, make_float2(ex2_approx(alo.x), ex2_approx(alo.y)));
-            const float2 chi = __fmul2_rn(am, make_float2(ex2_approx(ahi.x), ex2_approx(ahi.y)));
-            reinterpret_cast<float4*>(ct)[kk * 8 + a] = make_float4(clo.x, clo.y, chi.x, chi.y);
+            const float2 xlo = __fmul2_rn(jlo, __ffma2_rn(sa2, __fadd2_rn(d22, jlo), u2));
+            const float2 xhi = __fmul2_rn(jhi, __ffma2_rn(sa2, __fadd2_rn(d22, jhi), u2));
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+                const float iv = (ii ? 0.5f : -0.5f) * v;
+                const float2 alo = __fadd2_rn(xlo, make_float2(iv, iv)), ahi = __fadd2_rn(xhi, make_float2(iv, iv));
+                reinterpret_cast<float4*>(ct)[(kk * 2 + ii) * G::GPR + a] =
+                    make_float4(amp * ex2_approx(alo.x), amp * ex2_approx(alo.y), amp * ex2_approx(ahi.x), amp * ex2_approx(ahi.y));
+            }
         }
     }
     __syncwarp();
-    const int mine = ((colA - pan * G::PW) >> 2) & 7;   // this lane's group-A anchor
-    const float xaA = (float)colA + 1.5f, xaB = (float)colB + 1.5f;
+    const int mine = lane % G::GPR;   // this lane's anchor
+    const float xa = (float)(pan * G::PW + 4 * mine) + 1.5f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const float4 v = reinterpret_cast<const float4*>(ct)[k * 8 + mine];
-        lk.C[k][0] = make_float2(v.x, v.y);
-        lk.C[k][1] = make_float2(v.z, v.w);
-        lk.dxa[k] = make_float2(xaA - cf.x0[k], xaB - cf.x0[k]);
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+            const float4 v = reinterpret_cast<const float4*>(ct)[(k * 2 + ii) * G::GPR + mine];
+            lk.C[k][2 * ii] = make_float2(v.x, v.y);
+            lk.C[k][2 * ii + 1] = make_float2(v.z, v.w);
+        }
+        lk.dxa[k] = xa - cf.x0[k];
     }
 }
 
 template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND, int TM = 0>
 __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<NB>& lk, float2& s0, float2& s1,
-                                               int& i, int i1, StepPtrs& sp, int colA, int colB) {
+                                               int& i, int i1, StepPtrs& sp) {
     using G = Geo<NX>;
     using T = Tab<NB>;
     constexpr int K = 2 * NB;
@@ -810,19 +782,19 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
     uint32_t tm = sp.tm;
 #pragma unroll kLoopUnroll
     for (; i < i1; ++i) {
-        float4 dA, dB, wA, wB;
+        float4 d0, d1, w0, w1;
         uint32_t tv[16];
         if (TM == 1) {
             tmem_ld16_issue(tm, tv);
         } else if (TM == 2) {
             tmem_ld8_issue(tm, tv);
-            dA = *reinterpret_cast<const float4*>(dp + colA);
-            dB = *reinterpret_cast<const float4*>(dp + colB);
+            d0 = *reinterpret_cast<const float4*>(dp);
+            d1 = *reinterpret_cast<const float4*>(dp + NX);
         } else {
-            dA = *reinterpret_cast<const float4*>(dp + colA);
-            dB = *reinterpret_cast<const float4*>(dp + colB);
-            wA = *reinterpret_cast<const float4*>(wp + colA);
-            wB = *reinterpret_cast<const float4*>(wp + colB);
+            d0 = *reinterpret_cast<const float4*>(dp);
+            d1 = *reinterpret_cast<const float4*>(dp + NX);
+            w0 = *reinterpret_cast<const float4*>(wp);
+            w1 = *reinterpret_cast<const float4*>(wp + NX);
         }
         float2 m[4];
 #pragma unroll
@@ -836,45 +808,39 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
             }
 #pragma unroll
             for (int c = (KIND == 2 ? 0 : 1); c < 2; ++c) {
-                const float4 RA = reinterpret_cast<const float4*>(rp + T::OFF_RA)[c];
-                const float4 RB = reinterpret_cast<const float4*>(rp + T::OFF_RB)[c];
-                const float2 sa2 = make_float2(cf.sa[c], cf.sa[c]);
+                const float4 T0 = reinterpret_cast<const float4*>(rp + T::OFF_T)[2 * c];
+                const float4 T1 = reinterpret_cast<const float4*>(rp + T::OFF_T)[2 * c + 1];
                 float2 u[4];
 #pragma unroll
                 for (int o = 0; o < NB; ++o) {
                     const int k = 2 * o + c;
-                    const float2 t = __ffma2_rn(sa2, lk.dxa[k], make_float2(rc[2 * k], rc[2 * k]));
-                    const float2 q = __ffma2_rn(lk.dxa[k], t, make_float2(rc[2 * k + 1], rc[2 * k + 1]));
-                    const float eA = ex2_approx(q.x), eB = ex2_approx(q.y);
-                    const float2 ea = make_float2(eA, eA), eb = make_float2(eB, eB);
-                    if (o == 0) {
-                        u[0] = __fmul2_rn(lk.C[k][0], ea); u[1] = __fmul2_rn(lk.C[k][1], ea);
-                        u[2] = __fmul2_rn(lk.C[k][0], eb); u[3] = __fmul2_rn(lk.C[k][1], eb);
-                    } else {
-                        u[0] = __ffma2_rn(lk.C[k][0], ea, u[0]); u[1] = __ffma2_rn(lk.C[k][1], ea, u[1]);
-                        u[2] = __ffma2_rn(lk.C[k][0], eb, u[2]); u[3] = __ffma2_rn(lk.C[k][1], eb, u[3]);
-                    }
+                    const float q = fmaf(lk.dxa[k], fmaf(cf.sa[c], lk.dxa[k], rc[2 * k]), rc[2 * k + 1]);
+                    const float e = ex2_approx(q);
+                    const float2 e2 = make_float2(e, e);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        u[p] = (o == 0) ? __fmul2_rn(lk.C[k][p], e2) : __ffma2_rn(lk.C[k][p], e2, u[p]);
                 }
-                m[0] = __ffma2_rn(make_float2(RA.x, RA.y), u[0], m[0]); m[1] = __ffma2_rn(make_float2(RA.z, RA.w), u[1], m[1]);
-                m[2] = __ffma2_rn(make_float2(RB.x, RB.y), u[2], m[2]); m[3] = __ffma2_rn(make_float2(RB.z, RB.w), u[3], m[3]);
+                m[0] = __ffma2_rn(make_float2(T0.x, T0.y), u[0], m[0]); m[1] = __ffma2_rn(make_float2(T0.z, T0.w), u[1], m[1]);
+                m[2] = __ffma2_rn(make_float2(T1.x, T1.y), u[2], m[2]); m[3] = __ffma2_rn(make_float2(T1.z, T1.w), u[3], m[3]);
             }
         }
         if (TM == 1) {
             tmem_ld16_wait(tv);
-            dA = make_float4(__uint_as_float(tv[0]), __uint_as_float(tv[1]), __uint_as_float(tv[2]), __uint_as_float(tv[3]));
-            dB = make_float4(__uint_as_float(tv[4]), __uint_as_float(tv[5]), __uint_as_float(tv[6]), __uint_as_float(tv[7]));
+            d0 = make_float4(__uint_as_float(tv[0]), __uint_as_float(tv[1]), __uint_as_float(tv[2]), __uint_as_float(tv[3]));
+            d1 = make_float4(__uint_as_float(tv[4]), __uint_as_float(tv[5]), __uint_as_float(tv[6]), __uint_as_float(tv[7]));
             tm += 16;
         } else if (TM == 2) {
             tmem_ld8_wait(tv);
             tm += 8;
         }
         if (TM) {
-            wA = make_float4(__uint_as_float(tv[8]), __uint_as_float(tv[9]), __uint_as_float(tv[10]), __uint_as_float(tv[11]));
-            wB = make_float4(__uint_as_float(tv[12]), __uint_as_float(tv[13]), __uint_as_float(tv[14]), __uint_as_float(tv[15]));
+            w0 = make_float4(__uint_as_float(tv[8]), __uint_as_float(tv[9]), __uint_as_float(tv[10]), __uint_as_float(tv[11]));
+            w1 = make_float4(__uint_as_float(tv[12]), __uint_as_float(tv[13]), __uint_as_float(tv[14]), __uint_as_float(tv[15]));
         }
-        finish_step<NX, STORE, PREP>(m, dA, dB, wA, wB, mp, colA, colB, s0, s1);
+        finish_step<NX, STORE, PREP>(m, d0, d1, w0, w1, mp, s0, s1);
         if (STORE) mp += G::RG * NX;
-        rp += G::RG * T::RS;
+        rp += G::BPS * T::RS;
         dp += G::RG * NX;
         wp += G::RG * NX;
     }
@@ -882,10 +848,10 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
 }
 
 // chi-square of one parameter vector over the stamp by ONE warp (TEAM = 1), or this warp's share
-// of it (TEAM > 1: warp `tw` takes every TEAM-th row step; the caller adds the partials in a fixed
-// order).  Builds the row and column tables in `scratch` (Scratch<NB, NY, TEAM>::FLOATS floats of
-// this warp's own shared memory) itself.  `exps` counts the component evaluations (pixels x
-// components) the far-field culling left to do.
+// of it (TEAM > 1: warp `tw` takes every TEAM-th warp step; the caller adds the partials in a fixed
+// order).  Builds the block and column tables in `scratch` (Scratch<NB, NX, NY, TEAM>::FLOATS
+// floats of this warp's own shared memory) itself.  `exps` counts the component evaluations
+// (pixels x components) the far-field culling left to do.
 template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1, int TM = 0>
 __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restrict__ scratch,
                                             const float* __restrict__ d, const float* __restrict__ w,
@@ -896,29 +862,24 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
     using R = Rows<NY, TEAM>;
     constexpr int K = 2 * NB;
     constexpr int TR = R::TR;
-    constexpr int STEPS = TR / G::RG;            // row steps per table (per panel)
+    constexpr int STEPS = TR / G::RG;            // warp steps per table (per panel)
     static_assert(TM == 0 || (TEAM == 1 && PREP), "the TMEM pixel store holds prepared stamps for whole-warp passes");
     static_assert(TM != 1 || (R::HALVES == 1 && G::PANELS == 1), "both planes fit the 512 TMEM columns up to 64 x 64 pixels");
-    constexpr int TM_STEP = TM == 1 ? 16 : 8;     // TMEM columns per row step
+    constexpr int TM_STEP = TM == 1 ? 16 : 8;     // TMEM columns per warp step
     static_assert(TR % G::RG == 0, "unsupported stamp height");
-    static_assert(STEPS % TEAM == 0, "team size must divide the row steps");
+    static_assert(STEPS % TEAM == 0, "team size must divide the warp steps");
     float* rt = scratch;
-    float* ct = scratch + Scratch<NB, NY, TEAM>::TAB;
-    const int c = lane % G::LPR, g = lane / G::LPR;
-    const int swap = (G::PW == 32) ? (g & 1) : 0;
+    float* ct = scratch + Scratch<NB, NX, NY, TEAM>::TAB;
+    const int a = lane % G::GPR, b = lane / G::GPR;
     double acc = 0.0;
     if (exps) *exps += cf.nexp;
 #pragma unroll 1
     for (int half = 0; half < R::HALVES; ++half) {
-        build_row_table<NB, NX, TR, TEAM>(rt, cf, lane, half * TR, tw);
-        const float* dh = d + half * TR * NX;
-        const float* wh = w + half * TR * NX;
-        float* mh = STORE ? model_out + half * TR * NX : nullptr;
+        if (cf.fast) build_row_table<NB, NX, TR, TEAM>(rt, cf, lane, half * TR, tw);
 #pragma unroll 1
         for (int pan = 0; pan < G::PANELS; ++pan) {
-            const int colA = pan * G::PW + 4 * c + (G::PW / 2) * swap;
-            const int colB = pan * G::PW + 4 * c + (G::PW / 2) * (1 - swap);
-            // segments of this panel, clipped to the row steps of this table:
+            const int off0 = (half * TR + 2 * b) * NX + pan * G::PW + 4 * a;   // the lane's block of warp step 0
+            // segments of this panel, clipped to the warp steps of this table:
             //   [0,wlo) none, [wlo,nlo) wings, [nlo,nhi1) all, [nhi1,whi1) wings, [whi1,STEPS) none
             const bool p1 = G::PANELS > 1 && pan > 0;   // (constant indices keep the coefficients in registers)
             int wlo = p1 ? cf.seg[1][0] : cf.seg[0][0], nlo = p1 ? cf.seg[1][1] : cf.seg[0][1];
@@ -931,50 +892,51 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
             float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
             if (cf.fast) {
                 LaneK<NB> lk;
-                coop_consts<NB, NX>(lk, ct, cf, lane, pan, colA, colB);
+                coop_consts<NB, NX>(lk, ct, cf, lane, pan);
                 if (TEAM == 1) {
                     // contiguous steps: the pointers run through the segments
-                    StepPtrs sp{rt + g * T::RS, dh + g * NX, wh + g * NX, STORE ? mh + g * NX : nullptr,
-                                tmem + (uint32_t)((half * G::PANELS + pan) * STEPS * TM_STEP)};
+                    StepPtrs sp{rt + b * T::RS, d + off0, w + off0, STORE ? model_out + off0 : nullptr,
+                                tmem + (uint32_t)((half * G::PANELS + pan) * STEPS * TM_STEP), 0.f};
                     int i = 0;
                     if (NX < 64) {
                         // 32-pixel stamps have no far field (set_cull is never called for them)
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 2, TM>(cf, lk, s0, s1, i, STEPS, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 2, TM>(cf, lk, s0, s1, i, STEPS, sp);
                     } else {
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 0, TM>(cf, lk, s0, s1, i, wlo, sp, colA, colB);
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 1, TM>(cf, lk, s0, s1, i, nlo, sp, colA, colB);
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 2, TM>(cf, lk, s0, s1, i, nhi1, sp, colA, colB);
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 1, TM>(cf, lk, s0, s1, i, whi1, sp, colA, colB);
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 0, TM>(cf, lk, s0, s1, i, STEPS, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 0, TM>(cf, lk, s0, s1, i, wlo, sp);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 1, TM>(cf, lk, s0, s1, i, nlo, sp);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 2, TM>(cf, lk, s0, s1, i, nhi1, sp);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 1, TM>(cf, lk, s0, s1, i, whi1, sp);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 0, TM>(cf, lk, s0, s1, i, STEPS, sp);
                     }
                 } else {
                     // a team member owns only STEPS/TEAM steps (no culling in teams): one dense step at a time;
-                    // its table holds just those rows
+                    // its table holds just those blocks
 #pragma unroll 1
                     for (int mth = 0; mth < STEPS / TEAM; ++mth) {
-                        const int r0 = (mth * TEAM + tw) * G::RG + g;
-                        StepPtrs sp{rt + (mth * G::RG + g) * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr, 0u};
+                        const int so = (mth * TEAM + tw) * G::RG * NX;
+                        StepPtrs sp{rt + (mth * G::BPS + b) * T::RS, d + off0 + so, w + off0 + so,
+                                    STORE ? model_out + off0 + so : nullptr, 0u, 0.f};
                         int i = 0;
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, 1, sp, colA, colB);
+                        row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, 1, sp);
                     }
                 }
             } else {
-                float2 xd[K][4];   // pixel pairs: (0,1) (2,3) of group A, (0,1) (2,3) of group B
-                const float fa = (float)colA, fb = (float)colB;
-                const float2 cols[4] = {make_float2(fa, fa + 1.f), make_float2(fa + 2.f, fa + 3.f),
-                                        make_float2(fb, fb + 1.f), make_float2(fb + 2.f, fb + 3.f)};
+                float2 xd[K][2];   // column offsets of the lane's pixel pairs (0,1) and (2,3)
+                const float fa = (float)(pan * G::PW + 4 * a);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const float2 nx0 = make_float2(-cf.x0[k], -cf.x0[k]);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) xd[k][j] = __fadd2_rn(cols[j], nx0);
+                    xd[k][0] = __fadd2_rn(make_float2(fa, fa + 1.f), nx0);
+                    xd[k][1] = __fadd2_rn(make_float2(fa + 2.f, fa + 3.f), nx0);
                 }
 #pragma unroll 1
                 for (int mth = 0; mth < STEPS / TEAM; ++mth) {
-                    const int r0 = (mth * TEAM + tw) * G::RG + g;
-                    StepPtrs sp{rt + (mth * G::RG + g) * T::RS, dh + r0 * NX, wh + r0 * NX, STORE ? mh + r0 * NX : nullptr, 0u};
+                    const int st = mth * TEAM + tw;
+                    const int so = st * G::RG * NX;
+                    StepPtrs sp{nullptr, d + off0 + so, w + off0 + so, STORE ? model_out + off0 + so : nullptr, 0u,
+                                (float)(half * TR + st * G::RG + 2 * b)};
                     int i = 0;
-                    row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, s0, s1, i, 1, sp, colA, colB);
+                    row_steps<NB, NX, NY, STORE, PREP>(cf, xd, s0, s1, i, 1, sp);
                 }
             }
             // FP32 partial sums of one panel (at most 16 steps x 8 pixels over 4 accumulators) -> FP64
@@ -985,52 +947,48 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
 }
 
 // Copy of the prepared stamp into the TMEM pixel store: called by warps 0..3 (one per TMEM lane
-// quadrant) after prep_stamp; row step i of the lane goes to columns 16 i .. 16 i + 15 in the order
-// the loop consumes them (data A, data B, weight A, weight B).
+// quadrant) after prep_stamp; warp step i of the lane goes to columns 16 i .. 16 i + 15 in the
+// order the loop consumes them (data row 0, data row 1, weight row 0, weight row 1).
 template <int NX, int NY>
 __device__ __forceinline__ void tmem_fill_stamp(uint32_t tmem_base, const float* __restrict__ sd,
                                                 const float* __restrict__ sw, int warp, int lane) {
     using G = Geo<NX>;
     static_assert(G::PANELS == 1, "one panel");
-    const int c = lane % G::LPR, g = lane / G::LPR;
-    const int swap = (G::PW == 32) ? (g & 1) : 0;
-    const int colA = 4 * c + (G::PW / 2) * swap, colB = 4 * c + (G::PW / 2) * (1 - swap);
+    const int a = lane % G::GPR, b = lane / G::GPR;
     const uint32_t addr = tmem_base + ((uint32_t)(32 * warp) << 16);
 #pragma unroll 1
     for (int i = 0; i < NY / G::RG; ++i) {
-        const int r = i * G::RG + g;
-        const float4 dA = *reinterpret_cast<const float4*>(sd + r * NX + colA);
-        const float4 dB = *reinterpret_cast<const float4*>(sd + r * NX + colB);
-        const float4 wA = *reinterpret_cast<const float4*>(sw + r * NX + colA);
-        const float4 wB = *reinterpret_cast<const float4*>(sw + r * NX + colB);
-        const float v[16] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w, wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+        const int o = (i * G::RG + 2 * b) * NX + 4 * a;
+        const float4 d0 = *reinterpret_cast<const float4*>(sd + o);
+        const float4 d1 = *reinterpret_cast<const float4*>(sd + o + NX);
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + o);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + o + NX);
+        const float v[16] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         tmem_st16(addr + 16 * i, v);
     }
     tmem_wait_st();
 }
 
-// 128-pixel stamps: only the weight plane fits (8 columns per row step, 4 tables x 2 panels x 8
+// 128-pixel stamps: only the weight plane fits (8 columns per warp step, 2 tables x 2 panels x 16
 // steps = 512 columns, the whole TMEM); the data plane stays in shared memory.  Same order as the
-// loop nest of warp_chi2: table, panel, row step.
+// loop nest of warp_chi2: table, panel, warp step.
 template <int NX, int NY>
 __device__ __forceinline__ void tmem_fill_weights(uint32_t tmem_base, const float* __restrict__ sw, int warp, int lane) {
     using G = Geo<NX>;
     using R = Rows<NY, 1>;
     constexpr int STEPS = R::TR / G::RG;
     static_assert(R::HALVES * G::PANELS * STEPS * 8 <= 512, "weight plane exceeds the TMEM columns");
-    const int c = lane % G::LPR, g = lane / G::LPR;
-    const int swap = (G::PW == 32) ? (g & 1) : 0;
+    const int a = lane % G::GPR, b = lane / G::GPR;
     const uint32_t addr = tmem_base + ((uint32_t)(32 * warp) << 16);
 #pragma unroll 1
     for (int hp = 0; hp < R::HALVES * G::PANELS; ++hp) {
         const int half = hp / G::PANELS, pan = hp % G::PANELS;
-        const int colA = pan * G::PW + 4 * c + (G::PW / 2) * swap, colB = pan * G::PW + 4 * c + (G::PW / 2) * (1 - swap);
 #pragma unroll 1
         for (int i = 0; i < STEPS; ++i) {
-            const int r = half * R::TR + i * G::RG + g;
-            const float4 wA = *reinterpret_cast<const float4*>(sw + r * NX + colA);
-            const float4 wB = *reinterpret_cast<const float4*>(sw + r * NX + colB);
-            const float v[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+            const int o = (half * R::TR + i * G::RG + 2 * b) * NX + pan * G::PW + 4 * a;
+            const float4 w0 = *reinterpret_cast<const float4*>(sw + o);
+            const float4 w1 = *reinterpret_cast<const float4*>(sw + o + NX);
+            const float v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
             tmem_st8(addr + (uint32_t)((hp * STEPS + i) * 8), v);
         }
     }

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pass_kernel(double* out, int pa
     unsigned e = 0;
     for (int p = 0; p < passes; ++p) {
         cf.x0[0] += 1e-4f;
-        acc += warp_chi2<NB, NX, NY, false, true, 1, (TM ? 1 : 0)>(cf, rt + warp * (Scratch<NB, NY>::FLOATS), sd, sw, nullptr, lane, 0, &e,
+        acc += warp_chi2<NB, NX, NY, false, true, 1, (TM ? 1 : 0)>(cf, rt + warp * (Scratch<NB, NX, NY>::FLOATS), sd, sw, nullptr, lane, 0, &e,
                                                             tbase + ((uint32_t)(32 * (warp & 3)) << 16));
     }
     if (lane == 0 && blockIdx.x == 0) out[warp] = acc;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pass_kernel(double* out, int pa
 
 template <bool TM, int WARPS>
 void run(const char* name, double* d, int sms, int khz) {
-    const int smem = (2 * 64 * 64 + 16 * 1920) * 4;
+    const int smem = (2 * 64 * 64 + 16 * 1408) * 4;
     cudaFuncSetAttribute(pass_kernel<TM, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int passes = 4000;
