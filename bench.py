@@ -402,15 +402,17 @@ def run_b200(a):
     fp32_nominal = 2.0 * sm_count * 128 * f_run * 1e6
     alg_flops = per_gpu * (7 * K + 4)
     comp_rate = exps_timed / secs / world                           # component evaluations / s / GPU
-    # lane operations the pixel loop issues: per component evaluation (6 NB + 4) / (4 NB) packed-lane
-    # FMA/MUL (anchor exponents, C*E sums, row factor), per pixel 2 (residual, square-accumulate)
-    lane_ops = comp_rate * (6 * NB + 4) / (4.0 * NB) + per_gpu * 2.0
+    # lane operations the pixel loop issues per lane and warp step (8 pixels) for an active class:
+    # 2 NB (anchor exponents) + 8 NB (C*E sums, packed) + 8 (block factor, packed) for 8 NB component
+    # evaluations, i.e. (10 NB + 8) / (8 NB) each; per pixel 2 more (residual, square-accumulate)
+    lane_ops = comp_rate * (10 * NB + 8) / (8.0 * NB) + per_gpu * 2.0
     ex2_alg = per_gpu * K
-    # exponentials really issued: one per 4-pixel group and component + row/column tables per update
+    # exponentials really issued: one per 2x4-pixel block and component + block/column tables per update
     upd_rate = per_gpu / (S * S)
-    tr = min(S, 64) if S < 128 else 32
-    tab_ex2 = (S // tr) * tr * 16 + (S // min(S, 64)) * (S // tr) * 32 * K
-    ex2_exec = comp_rate / 4.0 + upd_rate * tab_ex2
+    tr = min(S, 64)
+    pw = min(S, 64)
+    tab_ex2 = (S // 2) * 16 + (S // pw) * (S // tr) * (pw // 4) * K * 8
+    ex2_exec = comp_rate / 8.0 + upd_rate * tab_ex2
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
@@ -433,7 +435,7 @@ def run_b200(a):
             "component_evals_per_pixel_eval": comp_rate / per_gpu,
             "ex2_per_s": ex2_exec, "ex2_per_pixel_eval": ex2_exec / per_gpu,
             "note": "FP32 lane operations of the pixel loop only (tables, proposals and reductions are overhead): "
-                    "(6NB+4)/(4NB) per component evaluation + 2 per pixel; component evaluations from the device "
+                    "(10NB+8)/(8NB) per component evaluation + 2 per pixel; component evaluations from the device "
                     "counter (far-field culling skips the rest)",
         },
         "sfu": {

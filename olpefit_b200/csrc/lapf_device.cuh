@@ -383,7 +383,8 @@ struct Rows {
 template <int NB, int NX, int NY, int TEAM = 1>
 struct Scratch {
     static constexpr int TAB = Rows<NY, TEAM>::NBLK * Tab<NB>::RS;
-    static constexpr int CT = 2 * NB * 2 * Geo<NX>::GPR * 4;
+    static constexpr int CT1 = 2 * NB * 2 * Geo<NX>::GPR * 4;              // one panel
+    static constexpr int CT = CT1 * (TEAM > 1 ? Geo<NX>::PANELS : 1);      // teams keep all panels (team_consts)
     static constexpr int FLOATS = TAB + CT;
 };
 
@@ -718,6 +719,26 @@ struct LaneK {
     float2 C[K][4];      // pixel pairs: row 0 (-3/2,-1/2), row 0 (1/2,3/2), row 1 (-3/2,-1/2), row 1 (1/2,3/2)
 };
 
+// The 8 lane constants C_k,ij of one component at one anchor column (dxa = anchor - x0_k), rows
+// i = -1/2 (lo) and +1/2 (hi), columns j = -3/2, -1/2, 1/2, 3/2.
+__device__ __forceinline__ void block_consts(float amp, float dxa, float dy0, float sa, float sb, float sc,
+                                             float4& lo, float4& hi) {
+    const float u = sb * dy0, d2 = 2.f * dxa;
+    const float v = fmaf(sb, dxa, 2.f * (sc * dy0));
+    const float2 u2 = make_float2(u, u), sa2 = make_float2(sa, sa), d22 = make_float2(d2, d2);
+    const float2 jlo = make_float2(-1.5f, -0.5f), jhi = make_float2(0.5f, 1.5f);
+    const float2 xlo = __fmul2_rn(jlo, __ffma2_rn(sa2, __fadd2_rn(d22, jlo), u2));
+    const float2 xhi = __fmul2_rn(jhi, __ffma2_rn(sa2, __fadd2_rn(d22, jhi), u2));
+    const float hv = 0.5f * v;
+    const float2 m2 = make_float2(-hv, -hv), p2 = make_float2(hv, hv);
+    const float2 a0 = __fadd2_rn(xlo, m2), a1 = __fadd2_rn(xhi, m2), b0 = __fadd2_rn(xlo, p2), b1 = __fadd2_rn(xhi, p2);
+    lo = make_float4(amp * ex2_approx(a0.x), amp * ex2_approx(a0.y), amp * ex2_approx(a1.x), amp * ex2_approx(a1.y));
+    hi = make_float4(amp * ex2_approx(b0.x), amp * ex2_approx(b0.y), amp * ex2_approx(b1.x), amp * ex2_approx(b1.y));
+}
+
+template <int NB, int NX>
+__device__ __forceinline__ void read_consts(LaneK<NB>& lk, const float* __restrict__ ct, const Coef<NB>& cf, int lane, int pan);
+
 // The C_k,ij of the GPR anchors of a panel (columns 4a + 1.5), worked out once per proposal by the
 // warp -- one (anchor, component) pair per lane and round -- and handed round through the column
 // table ct[k][row of the block][a][4]; every lane then reads the 8K values of its own anchor.
@@ -738,24 +759,51 @@ __device__ __forceinline__ void coop_consts(LaneK<NB>& lk, float* __restrict__ c
             const int c = kk & 1;
             const float sa = c ? cf.sa[1] : cf.sa[0], sb = c ? cf.sb[1] : cf.sb[0], sc = c ? cf.sc[1] : cf.sc[0];
             const float dy0 = (c ? cf.y0[1] : cf.y0[0]) - y0;           // exactly 0 for the class's first component
-            const float dxa = ((float)(pan * G::PW + 4 * a) + 1.5f) - x0;
-            const float u = sb * dy0, d2 = 2.f * dxa;
-            const float v = fmaf(sb, dxa, 2.f * (sc * dy0));
-            const float2 u2 = make_float2(u, u), sa2 = make_float2(sa, sa), d22 = make_float2(d2, d2);
-            const float2 jlo = make_float2(-1.5f, -0.5f), jhi = make_float2(0.5f, 1.5f);
-            const float2 xlo = __fmul2_rn(jlo, __ffma2_rn(sa2, __fadd2_rn(d22, jlo), u2));
-            const float2 xhi = __fmul2_rn(jhi, __ffma2_rn(sa2, __fadd2_rn(d22, jhi), u2));
-#pragma unroll
-            for (int ii = 0; ii < 2; ++ii) {
-                const float iv = (ii ? 0.5f : -0.5f) * v;
-                const float2 alo = __fadd2_rn(xlo, make_float2(iv, iv)), ahi = __fadd2_rn(xhi, make_float2(iv, iv));
-                reinterpret_cast<float4*>(ct)[(kk * 2 + ii) * G::GPR + a] =
-                    make_float4(amp * ex2_approx(alo.x), amp * ex2_approx(alo.y), amp * ex2_approx(ahi.x), amp * ex2_approx(ahi.y));
-            }
+            float4 lo, hi;
+            block_consts(amp, ((float)(pan * G::PW + 4 * a) + 1.5f) - x0, dy0, sa, sb, sc, lo, hi);
+            reinterpret_cast<float4*>(ct)[(kk * 2) * G::GPR + a] = lo;
+            reinterpret_cast<float4*>(ct)[(kk * 2 + 1) * G::GPR + a] = hi;
         }
     }
     __syncwarp();
-    const int mine = lane % G::GPR;   // this lane's anchor
+    read_consts<NB, NX>(lk, ct, cf, lane, pan);
+}
+
+// Team form (TEAM warps share one walker): the constants are the same for every member, so the
+// team's TEAM*32 lanes work them out together, for all panels at once, into the column table of
+// the team's first warp; one named barrier, then every lane reads its anchor (read_consts).
+template <int NB, int NX, int TEAM>
+__device__ __forceinline__ void team_consts(float* __restrict__ tct, const Coef<NB>& cf, int lane, int tw, int bar_id) {
+    using G = Geo<NX>;
+    constexpr int K = 2 * NB;
+    constexpr int ITEMS = G::PANELS * G::GPR * K;
+#pragma unroll
+    for (int t0 = 0; t0 < ITEMS; t0 += TEAM * 32) {
+        const int t = t0 + tw * 32 + lane;
+        if (ITEMS % (TEAM * 32) == 0 || t < ITEMS) {
+            const int a = t % G::GPR, kk = (t / G::GPR) % K, pan = t / (G::GPR * K);
+            float amp = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k)
+                if (kk == k) { amp = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
+            const int c = kk & 1;
+            const float sa = c ? cf.sa[1] : cf.sa[0], sb = c ? cf.sb[1] : cf.sb[0], sc = c ? cf.sc[1] : cf.sc[0];
+            const float dy0 = (c ? cf.y0[1] : cf.y0[0]) - y0;
+            float4 lo, hi;
+            block_consts(amp, ((float)(pan * G::PW + 4 * a) + 1.5f) - x0, dy0, sa, sb, sc, lo, hi);
+            float4* o = reinterpret_cast<float4*>(tct) + pan * (K * 2 * G::GPR);
+            o[(kk * 2) * G::GPR + a] = lo;
+            o[(kk * 2 + 1) * G::GPR + a] = hi;
+        }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(TEAM * 32) : "memory");
+}
+
+template <int NB, int NX>
+__device__ __forceinline__ void read_consts(LaneK<NB>& lk, const float* __restrict__ ct, const Coef<NB>& cf, int lane, int pan) {
+    using G = Geo<NX>;
+    constexpr int K = 2 * NB;
+    const int mine = lane % G::GPR;
     const float xa = (float)(pan * G::PW + 4 * mine) + 1.5f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -856,7 +904,7 @@ template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1, int TM = 
 __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restrict__ scratch,
                                             const float* __restrict__ d, const float* __restrict__ w,
                                             float* __restrict__ model_out, int lane, int tw = 0,
-                                            unsigned* exps = nullptr, uint32_t tmem = 0) {
+                                            unsigned* exps = nullptr, uint32_t tmem = 0, int bar_id = 0) {
     using G = Geo<NX>;
     using T = Tab<NB>;
     using R = Rows<NY, TEAM>;
@@ -873,6 +921,9 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
     const int a = lane % G::GPR, b = lane / G::GPR;
     double acc = 0.0;
     if (exps) *exps += cf.nexp;
+    // (the scratch areas of a team's warps are contiguous: the team's column table is its first warp's)
+    float* tct = scratch - tw * Scratch<NB, NX, NY, TEAM>::FLOATS + Scratch<NB, NX, NY, TEAM>::TAB;
+    if (TEAM > 1 && cf.fast) team_consts<NB, NX, TEAM>(tct, cf, lane, tw, bar_id);
 #pragma unroll 1
     for (int half = 0; half < R::HALVES; ++half) {
         if (cf.fast) build_row_table<NB, NX, TR, TEAM>(rt, cf, lane, half * TR, tw);
@@ -892,7 +943,8 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
             float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
             if (cf.fast) {
                 LaneK<NB> lk;
-                coop_consts<NB, NX>(lk, ct, cf, lane, pan);
+                if (TEAM == 1) coop_consts<NB, NX>(lk, ct, cf, lane, pan);
+                else read_consts<NB, NX>(lk, tct + pan * Scratch<NB, NX, NY, TEAM>::CT1, cf, lane, pan);
                 if (TEAM == 1) {
                     // contiguous steps: the pointers run through the segments
                     StepPtrs sp{rt + b * T::RS, d + off0, w + off0, STORE ? model_out + off0 : nullptr,
