@@ -41,7 +41,7 @@ extern "C" {
  * below 2^-24 of the floor (default: such far-field rows are skipped; results agree to FP32 rounding) */
 #define LAPF_FLAG_NO_CULL 1
 /* lapf_problem.flags: always take the plain pixel loop (one exponential per pixel and component)
- * instead of the factorised one (one exponential per 4-pixel group and component).
+ * instead of the factorised one (one exponential per 2x4-pixel block and component).
  * The factorised loop falls back to the plain one by itself for vectors outside its safe range;
  * this switch exists to compare the two. */
 #define LAPF_FLAG_PLAIN_LOOP 2

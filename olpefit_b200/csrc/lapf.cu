@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
 // the staged frame.  Everything that is scalar work per walker -- random numbers, proposal,
 // coefficients of the trial vector, culling bounds, accept/reject, counters, chain row -- is done
 // with ONE WALKER PER LANE, once per round, and costs 1/LW of a warp instruction per update.  In
-// between, the warp evaluates the trial vectors one after the other (a "pass": row table, lane
+// between, the warp evaluates the trial vectors one after the other (a "pass": block table, lane
 // constants, pixel loop, butterfly sum), reading each walker's coefficients from its
 // shared-memory image.  FP64 state lives in global memory (L1/L2 resident: one parameter read
 // and at most one written per update).  The arithmetic per walker is the one of run_walker: chains

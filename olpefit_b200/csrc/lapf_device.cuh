@@ -5,8 +5,8 @@
 //                   segments, safe-range flag; CoefImg its shared-memory image
 //   warp_chi2<>     fused model / residual / square / reduce over one stamp by ONE warp
 //                   (replaces build_analytical_model + chi_squared, apf_step2.py:78-137):
-//                   row table + column table -> factorised loop (row_steps_fast: one exponential
-//                   per 4-pixel group and component) or plain loop (row_steps: one per pixel)
+//                   block table + column table -> factorised loop (row_steps_fast: one exponential
+//                   per 2x4-pixel block and component) or plain loop (row_steps: one per pixel)
 //   tmem_*          tensor memory as a per-lane pixel store (tcgen05.alloc / st / ld)
 //   philox / draws  counter-based random stream (replaces numpy's global MT, apf_step2.py:64,68,143,302)
 //
