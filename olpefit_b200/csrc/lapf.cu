@@ -363,7 +363,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         // in a team the update time is set by the warp with the busiest rows: culling cannot help there
         if (NX >= 64 && TEAM == 1 && a.cull) set_cull<NB, NX, NY, TEAM>(cf, lane); else no_cull<NB, NX, NY, TEAM>(cf);
         unsigned e_upd = 0;
-        double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw, &e_upd, 0u, 1 + team);   // :314-316
+        double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw, &e_upd);   // :314-316
         n_exps += e_upd;
         if (TEAM > 1) {
             double* slot_p = team_part + (u & 1) * TEAM;       // double-buffered: one barrier per update

@@ -383,8 +383,7 @@ struct Rows {
 template <int NB, int NX, int NY, int TEAM = 1>
 struct Scratch {
     static constexpr int TAB = Rows<NY, TEAM>::NBLK * Tab<NB>::RS;
-    static constexpr int CT1 = 2 * NB * 2 * Geo<NX>::GPR * 4;              // one panel
-    static constexpr int CT = CT1 * (TEAM > 1 ? Geo<NX>::PANELS : 1);      // teams keep all panels (team_consts)
+    static constexpr int CT = 2 * NB * 2 * Geo<NX>::GPR * 4;
     static constexpr int FLOATS = TAB + CT;
 };
 
@@ -769,34 +768,23 @@ __device__ __forceinline__ void coop_consts(LaneK<NB>& lk, float* __restrict__ c
     read_consts<NB, NX>(lk, ct, cf, lane, pan);
 }
 
-// Team form (TEAM warps share one walker): the constants are the same for every member, so the
-// team's TEAM*32 lanes work them out together, for all panels at once, into the column table of
-// the team's first warp; one named barrier, then every lane reads its anchor (read_consts).
-template <int NB, int NX, int TEAM>
-__device__ __forceinline__ void team_consts(float* __restrict__ tct, const Coef<NB>& cf, int lane, int tw, int bar_id) {
+// The same numbers without the exchange: every lane works out the 8K constants of its own anchor
+// (4x the arithmetic, but no shared-memory round trip) -- for team members, where the latency of
+// one update is what counts.
+template <int NB, int NX>
+__device__ __forceinline__ void own_consts(LaneK<NB>& lk, const Coef<NB>& cf, int lane, int pan) {
     using G = Geo<NX>;
     constexpr int K = 2 * NB;
-    constexpr int ITEMS = G::PANELS * G::GPR * K;
+    const float xa = (float)(pan * G::PW + 4 * (lane % G::GPR)) + 1.5f;
 #pragma unroll
-    for (int t0 = 0; t0 < ITEMS; t0 += TEAM * 32) {
-        const int t = t0 + tw * 32 + lane;
-        if (ITEMS % (TEAM * 32) == 0 || t < ITEMS) {
-            const int a = t % G::GPR, kk = (t / G::GPR) % K, pan = t / (G::GPR * K);
-            float amp = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
-#pragma unroll
-            for (int k = 1; k < K; ++k)
-                if (kk == k) { amp = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
-            const int c = kk & 1;
-            const float sa = c ? cf.sa[1] : cf.sa[0], sb = c ? cf.sb[1] : cf.sb[0], sc = c ? cf.sc[1] : cf.sc[0];
-            const float dy0 = (c ? cf.y0[1] : cf.y0[0]) - y0;
-            float4 lo, hi;
-            block_consts(amp, ((float)(pan * G::PW + 4 * a) + 1.5f) - x0, dy0, sa, sb, sc, lo, hi);
-            float4* o = reinterpret_cast<float4*>(tct) + pan * (K * 2 * G::GPR);
-            o[(kk * 2) * G::GPR + a] = lo;
-            o[(kk * 2 + 1) * G::GPR + a] = hi;
-        }
+    for (int k = 0; k < K; ++k) {
+        const int c = k & 1;
+        lk.dxa[k] = xa - cf.x0[k];
+        float4 lo, hi;
+        block_consts(cf.amp[k], lk.dxa[k], cf.y0[c] - cf.y0[k], cf.sa[c], cf.sb[c], cf.sc[c], lo, hi);
+        lk.C[k][0] = make_float2(lo.x, lo.y); lk.C[k][1] = make_float2(lo.z, lo.w);
+        lk.C[k][2] = make_float2(hi.x, hi.y); lk.C[k][3] = make_float2(hi.z, hi.w);
     }
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(TEAM * 32) : "memory");
 }
 
 template <int NB, int NX>
@@ -904,7 +892,7 @@ template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1, int TM = 
 __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restrict__ scratch,
                                             const float* __restrict__ d, const float* __restrict__ w,
                                             float* __restrict__ model_out, int lane, int tw = 0,
-                                            unsigned* exps = nullptr, uint32_t tmem = 0, int bar_id = 0) {
+                                            unsigned* exps = nullptr, uint32_t tmem = 0) {
     using G = Geo<NX>;
     using T = Tab<NB>;
     using R = Rows<NY, TEAM>;
@@ -921,9 +909,6 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
     const int a = lane % G::GPR, b = lane / G::GPR;
     double acc = 0.0;
     if (exps) *exps += cf.nexp;
-    // (the scratch areas of a team's warps are contiguous: the team's column table is its first warp's)
-    float* tct = scratch - tw * Scratch<NB, NX, NY, TEAM>::FLOATS + Scratch<NB, NX, NY, TEAM>::TAB;
-    if (TEAM > 1 && cf.fast) team_consts<NB, NX, TEAM>(tct, cf, lane, tw, bar_id);
 #pragma unroll 1
     for (int half = 0; half < R::HALVES; ++half) {
         if (cf.fast) build_row_table<NB, NX, TR, TEAM>(rt, cf, lane, half * TR, tw);
@@ -943,8 +928,7 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
             float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
             if (cf.fast) {
                 LaneK<NB> lk;
-                if (TEAM == 1) coop_consts<NB, NX>(lk, ct, cf, lane, pan);
-                else read_consts<NB, NX>(lk, tct + pan * Scratch<NB, NX, NY, TEAM>::CT1, cf, lane, pan);
+                if (TEAM == 1) coop_consts<NB, NX>(lk, ct, cf, lane, pan); else own_consts<NB, NX>(lk, cf, lane, pan);
                 if (TEAM == 1) {
                     // contiguous steps: the pointers run through the segments
                     StepPtrs sp{rt + b * T::RS, d + off0, w + off0, STORE ? model_out + off0 : nullptr,
