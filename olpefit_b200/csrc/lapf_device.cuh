@@ -387,43 +387,58 @@ struct Scratch {
     static constexpr int FLOATS = TAB + CT;
 };
 
+// A block's entry is 2 + K/2 independent 16-byte pieces (K/2 component pairs, 4 (class, row)
+// factor quadruples).  Team members, whose tables have 8 blocks or fewer, spread the pieces of a
+// block over 4 lanes, with the same instruction stream in every lane (the piece is picked with
+// selects): a quarter of the instructions and of the serialised MUFUs on the latency path of an
+// update.  (Whole-warp passes keep one block per lane: on 32-pixel stamps, the only case with lanes
+// to spare, the split was not faster.)
 template <int NB, int NX, int TR, int TEAM>
 __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Coef<NB>& cf, int lane, int row0, int tw) {
     using G = Geo<NX>;
     using T = Tab<NB>;
     constexpr int K = 2 * NB;
+    constexpr int NQ = K / 2;                         // component pairs (narrow, wide) = objects
     constexpr int NBLK = TR / 2 / TEAM;
+    constexpr int SPLIT = (TEAM == 1 || NBLK >= 32) ? 1 : (NBLK >= 16 ? 2 : 4);
     __syncwarp();   // readers of the previous table are done
 #pragma unroll
-    for (int j0 = 0; j0 < NBLK; j0 += 32) {
-        const int jb = j0 + lane;                  // local block: warp step jb / BPS of this warp, block jb % BPS
-        if (NBLK % 32 == 0 || jb < NBLK) {
+    for (int j0 = 0; j0 < NBLK * SPLIT; j0 += 32) {
+        const int idx = j0 + lane;
+        if ((NBLK * SPLIT) % 32 == 0 || idx < NBLK * SPLIT) {
+            const int jb = idx / SPLIT, part = idx % SPLIT;   // local block: warp step jb / BPS of this warp, block jb % BPS
             const int step = (jb / G::BPS) * TEAM + tw;
             const float yb = (float)(row0 + step * G::RG + 2 * (jb % G::BPS)) + 0.5f;
             float4* o = reinterpret_cast<float4*>(rt + jb * T::RS);
-            float v[2 * K];
+            // component pairs q = part, part + SPLIT, ...: (sb dyb, sc dyb^2) of the object's core and wing
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const float yd = yb - cf.y0[k];
-                v[2 * k] = cf.sb[k & 1] * yd;
-                v[2 * k + 1] = (cf.sc[k & 1] * yd) * yd;
+            for (int q0 = 0; q0 < NQ; q0 += SPLIT) {
+                const int q = q0 + part;
+                if (NQ % SPLIT == 0 || q < NQ) {
+                    float y0a = cf.y0[2 * q0], y0b = cf.y0[2 * q0 + 1];
+#pragma unroll
+                    for (int t = 1; t < SPLIT; ++t)
+                        if (q0 + t < NQ && part == t) { y0a = cf.y0[2 * (q0 + t)]; y0b = cf.y0[2 * (q0 + t) + 1]; }
+                    const float yda = yb - y0a, ydb = yb - y0b;
+                    o[q] = make_float4(cf.sb[0] * yda, (cf.sc[0] * yda) * yda, cf.sb[1] * ydb, (cf.sc[1] * ydb) * ydb);
+                }
             }
-#pragma unroll
-            for (int q = 0; q < 2 * K / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            // factor quadruples pr = 2 c + ii = part, part + SPLIT, ...
             const float2 jlo = make_float2(-1.5f, -0.5f), jhi = make_float2(0.5f, 1.5f);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const float p = v[2 * c];                       // sb_c * dyb_c (component c is the class's first)
-                const float s = (cf.sc[c] * (yb - cf.y0[c])) * 2.f;
-                const float g = 0.25f * cf.sc[c];
-#pragma unroll
-                for (int ii = 0; ii < 2; ++ii) {
-                    const float i = ii ? 0.5f : -0.5f;
-                    const float pj = fmaf(i, cf.sb[c], p), base = fmaf(i, s, g);
-                    const float2 pj2 = make_float2(pj, pj), b2 = make_float2(base, base);
-                    const float2 alo = __ffma2_rn(jlo, pj2, b2), ahi = __ffma2_rn(jhi, pj2, b2);
-                    o[T::OFF_T / 4 + 2 * c + ii] = make_float4(ex2_approx(alo.x), ex2_approx(alo.y), ex2_approx(ahi.x), ex2_approx(ahi.y));
-                }
+            for (int p0 = 0; p0 < 4; p0 += SPLIT) {
+                const int pr = p0 + part;
+                const bool c = (pr >> 1) != 0, hi = (pr & 1) != 0;
+                const float sbc = c ? cf.sb[1] : cf.sb[0], scc = c ? cf.sc[1] : cf.sc[0];
+                const float yd = yb - (c ? cf.y0[1] : cf.y0[0]);
+                const float p = sbc * yd;                       // sb_c * dyb_c
+                const float sy = (scc * yd) * 2.f;
+                const float g = 0.25f * scc;
+                const float i = hi ? 0.5f : -0.5f;
+                const float pj = fmaf(i, sbc, p), base = fmaf(i, sy, g);
+                const float2 pj2 = make_float2(pj, pj), b2 = make_float2(base, base);
+                const float2 alo = __ffma2_rn(jlo, pj2, b2), ahi = __ffma2_rn(jhi, pj2, b2);
+                o[T::OFF_T / 4 + pr] = make_float4(ex2_approx(alo.x), ex2_approx(alo.y), ex2_approx(ahi.x), ex2_approx(ahi.y));
             }
         }
     }
