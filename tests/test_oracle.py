@@ -123,3 +123,29 @@ def test_run_chain_rules():
     prev = np.vstack([truth[None], r2.rows[1:-1, :-1]])
     changed = np.any(r2.rows[1:, :-1] != prev, axis=1)
     assert int(changed.sum()) == int(r2.accepts.sum()) < r2.n_updates
+
+
+def test_block_factorisation_identity():
+    """The algebra behind the device's factorised pixel loop, restated in
+    float64: around the centre (xa, yb) of a 2 x 4 pixel block every component value is
+    E_k * C_k,ij * T_c,ij with one exponential per block (E), lane constants (C) and block factors
+    shared by the shape class (T).  Checked against the oracle's own component evaluation."""
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        sx, sy, th = rng.uniform(1.5, 7.0), rng.uniform(1.5, 7.0), rng.uniform(-1.6, 1.6)
+        a = 0.5 * (np.cos(th) ** 2 / sx ** 2 + np.sin(th) ** 2 / sy ** 2)
+        b = 0.5 * (np.sin(2 * th) / sx ** 2 - np.sin(2 * th) / sy ** 2)
+        c = 0.5 * (np.sin(th) ** 2 / sx ** 2 + np.cos(th) ** 2 / sy ** 2)
+        sa, sb, sc = -a * np.log2(np.e), -b * np.log2(np.e), -c * np.log2(np.e)   # q = sa dx^2 + sb dx dy + sc dy^2
+        amp = rng.uniform(10, 1e4)
+        x0c, y0c = rng.uniform(20, 44, 2)            # first component of the class
+        x0k, y0k = x0c + rng.normal(0, 6), y0c + rng.normal(0, 6)
+        xa, yb = 4 * rng.integers(0, 16) + 1.5, 2 * rng.integers(0, 32) + 0.5
+        dxa, dyb_c, dy0 = xa - x0k, yb - y0c, y0c - y0k
+        E = 2.0 ** (sa * dxa ** 2 + sb * dxa * (yb - y0k) + sc * (yb - y0k) ** 2)
+        for i in (-0.5, 0.5):
+            for j in (-1.5, -0.5, 0.5, 1.5):
+                C = amp * 2.0 ** (j * (sa * (2 * dxa + j) + sb * dy0) + i * (sb * dxa + 2 * sc * dy0))
+                T = 2.0 ** (j * sb * (dyb_c + i) + 2 * i * sc * dyb_c + sc / 4)
+                direct = amp * orc.gaussian2d(np.array([[xa + j]]), np.array([[yb + i]]), 1.0, x0k, y0k, sx, sy, th)[0, 0]
+                assert E * C * T == pytest.approx(direct, rel=1e-11)
