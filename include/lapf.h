@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define LAPF_ABI_VERSION 1
+#define LAPF_ABI_VERSION 2
 #define LAPF_MAX_PARAMS 19
 /* lapf_problem.flags: evaluate every component at every pixel, also where its value is provably
  * below 2^-24 of the floor (default: such far-field rows are skipped; results agree to FP32 rounding) */
@@ -126,7 +126,8 @@ int lapf_sampler_destroy(lapf_sampler* s);
  * stream of epochs reuse one handle without reallocating device memory. */
 int lapf_sampler_reset(lapf_sampler* s, const double* init_params, uint64_t seed, void* stream);
 
-/* Checkpoint / resume.  A walker is (parameters, chi-square, counters, moments, update count) and
+/* Checkpoint / resume.  A walker is (parameters, chi-square, counters, moments, update count; the
+ * batch adds its seed and current jump widths) and
  * its random stream is a pure function of (seed, walker id, update count), so a saved blob restores
  * the batch exactly: run(a); save; ...; load; run(b) gives the bits of run(a+b).  The blob is a
  * device buffer of lapf_sampler_checkpoint_bytes() bytes owned by the caller; load() expects a
@@ -147,8 +148,23 @@ int64_t lapf_sampler_rows_for(const lapf_sampler* s, int64_t n_updates);
  *   chain_out  device [rows][n_walkers][P+1] double (P parameters then chi-square, the column
  *              order of <rank>_finalarray_mpi.csv, apf_step2.py:346-351), or NULL to record
  *              nothing; rows_cap = capacity in rows (must be >= lapf_sampler_rows_for). */
-int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int64_t rows_cap,
+int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, void* chain_out, int64_t rows_cap,
                      void* stream);
+
+/* Format of the rows lapf_sampler_run writes to chain_out (default LAPF_CHAIN_F64):
+ *   LAPF_CHAIN_F64        double [rows][n_walkers][P+1], the values themselves
+ *   LAPF_CHAIN_F32_DELTA  float  [rows][n_walkers][P+1], value minus the walker's starting point
+ *                         (lapf_sampler_start): half the bytes that leave the device, and no
+ *                         precision lost where it matters -- a chain stays within a few jump
+ *                         widths of its start, so the float carries the difference to ~1e-7 of
+ *                         itself (positions: 512.3 +- 0.003 would keep only 2e-5 as plain floats).
+ * Replaces the text rows of apf_step2.py:346-360 for batches of 10^4 .. 10^6 walkers. */
+#define LAPF_CHAIN_F64 0
+#define LAPF_CHAIN_F32_DELTA 1
+int lapf_sampler_set_chain_format(lapf_sampler* s, int32_t format);
+/* The starting point of every walker and its chi-square: start_out device double [n_walkers][P+1]
+ * (the reference point of LAPF_CHAIN_F32_DELTA rows and of the running moments). */
+int lapf_sampler_start(lapf_sampler* s, double* start_out, void* stream);
 
 /* Current state: state_out device [n_walkers][P+1] double; counters device [n_walkers][P]
  * uint32 each (total_tries / total_accept of apf_step2.py:276,304,323).  Any may be NULL. */
@@ -168,6 +184,24 @@ int lapf_sampler_state(lapf_sampler* s, double* state_out, uint32_t* tries_out,
  *   counts_out  device int64[F+1] or NULL: walkers per frame, then rows recorded per walker */
 int lapf_sampler_stats(lapf_sampler* s, int64_t* totals_out, double* moments_out,
                        int64_t* counts_out, void* stream);
+
+/* K4b -- separation / position angle of the recorded rows without the chain (apf_step3.py:255-256,
+ * 283-291: sep = sqrt(dx^2 + dy^2), pa = degrees(atan2(-dx, dy)) of each companion relative to the
+ * first object; 3-body: both pairs, 3body/apf_step3_3body.py:273-276,318-324; medians and standard
+ * deviations are what :436-437 report).  Once enabled, every recorded row of every walker enters,
+ * per frame and companion, two fixed-width histograms (separation in PIXELS, position angle in
+ * degrees; n_bins bins centred on a per-frame centre value, plus an underflow and an overflow bin)
+ * and the walker's running sums.  Histograms are integer counts: they add up exactly over walkers
+ * and over GPUs (all-reduce them; give every rank the same centres).
+ *   centers    device double [F][nbody-1][2] (separation, position angle) or NULL: the starting
+ *              point of the first walker of each frame in THIS batch
+ * Enable before the first lapf_sampler_run; lapf_sampler_reset zeroes the sketches. */
+int lapf_sampler_sketch_enable(lapf_sampler* s, int32_t n_bins, double sep_bin_pixels, double pa_bin_degrees,
+                               const double* centers, void* stream);
+/*   hist_out     device uint32 [F][nbody-1][2][n_bins+2] or NULL (bin 0: below range, bin n_bins+1: above / nan)
+ *   summary_out  device double [F][nbody-1][2][4] or NULL: centre, sum of (value - centre), sum of
+ *                (value - centre)^2, number of values (position-angle differences wrapped to +-180) */
+int lapf_sampler_sketch(lapf_sampler* s, uint32_t* hist_out, double* summary_out, void* stream);
 
 /* Total update count so far (same for every walker). */
 int64_t lapf_sampler_count(const lapf_sampler* s);
@@ -200,10 +234,20 @@ int lapf_frame_prep(const float* frames, int32_t n_frames, int32_t fy, int32_t f
                     const int32_t* origin, int32_t ny, int32_t nx, double satlevel,
                     double readnoise, float* data_out, float* weight_out, void* stream);
 
+/* The part of the reference's whole-frame chi-square that lies OUTSIDE the cut-outs
+ * (lapf_problem.outside): per frame sum w, sum w*d, sum w*d^2 over those pixels, with the weight
+ * map of lapf_frame_prep, in FP64 and a fixed order.
+ *   cut          device [F][2] (x, y) of each cut-out INSIDE its frame array
+ *   outside_out  device double [F][3] */
+int lapf_frame_outside(const float* frames, int32_t n_frames, int32_t fy, int32_t fx, const int32_t* cut,
+                       int32_t ny, int32_t nx, double satlevel, double readnoise, double* outside_out,
+                       void* stream);
+
 /* The sampler's random stream for updates first_update .. first_update+n-1 of one walker, in the
  * reference's draw order (apf_step2.py:302 index, :64/:68 normal, :143 uniform): parameter index,
  * standard normal, natural log of the uniform.  Device outputs of length n.  Philox4x32-10 with
- * key = (seed low 32 bits, walker id) and counter = (update low, update high, seed high, 'LAPF'). */
+ * key = (seed low 32 bits, walker id) and counter = (update low, update high, seed high, 'LAPF');
+ * the normal is Box-Muller of two 32-bit words, the uniform carries 53 bits like numpy's rand(). */
 int lapf_philox_draws(uint64_t seed, uint64_t walker_id, uint64_t first_update, int32_t n, int32_t nparam,
                       int32_t* index_out, double* normal_out, double* log_uniform_out, void* stream);
 

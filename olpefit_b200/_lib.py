@@ -45,6 +45,12 @@ SYMBOLS = {
     "lapf_sampler_set_widths": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "lapf_sampler_rows_for": (C.c_int64, [C.c_void_p, C.c_int64]),
     "lapf_sampler_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "lapf_sampler_set_chain_format": (C.c_int, [C.c_void_p, C.c_int32]),
+    "lapf_sampler_start": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lapf_sampler_sketch_enable": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "lapf_sampler_sketch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lapf_frame_outside": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                     C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "lapf_sampler_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lapf_sampler_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lapf_sampler_count": (C.c_int64, [C.c_void_p]),
@@ -70,8 +76,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = lib_path()
-    if _build.is_stale():
+    path = os.environ.get("LAPF_LIB") or lib_path()      # LAPF_LIB: an experimental build of the same sources
+    if path == lib_path() and _build.is_stale():
         try:
             _build.build()
         except Exception as exc:  # no nvcc on this box: use what is there, or fail loudly
@@ -86,7 +92,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.lapf_abi_version() != 1:
+    if lib.lapf_abi_version() != 2:
         raise LapfError("liblapf ABI version mismatch")
     _lib = lib
     return lib

@@ -103,18 +103,47 @@ def write_acceptance(path, accepts, tries):
 
 
 class PackedChainWriter:
-    """Packed binary chain: float64 [row][walker][P+1] appended segment by segment to
-    ``<base>.bin`` with a JSON sidecar ``<base>.json``; for batches of 10^4..10^6 walkers where
-    one text file per walker is not workable.  ``unpack_to_csv`` converts back."""
+    """Packed binary chain: [row][walker][P+1] appended segment by segment to ``<base>.bin`` with a
+    JSON sidecar ``<base>.json``; for batches of 10^4..10^6 walkers where one text file per walker
+    is not workable.  dtype 'float64' holds the values; 'float32' holds differences from the
+    walkers' starting points, which are stored once as float64 in ``<base>.start.bin``
+    (LAPF_CHAIN_F32_DELTA).  ``resume=True`` appends to an existing file of the same shape (the
+    sidecar tells the row count so far).  ``read_packed`` / ``unpack_to_csv`` convert back."""
 
-    def __init__(self, base, n_walkers, n_cols, meta=None):
+    def __init__(self, base, n_walkers, n_cols, meta=None, dtype="float64", start=None, resume=False):
         self.base, self.n_walkers, self.n_cols = base, int(n_walkers), int(n_cols)
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype("float64"), np.dtype("float32")):
+            raise ValueError("packed chains are float64 or float32 (differences from the start)")
         self.rows = 0
         self.meta = dict(meta or {})
-        self.fh = open(base + ".bin", "wb")
+        if resume:
+            with open(base + ".json") as fh:
+                old = json.load(fh)
+            if (old["n_walkers"], old["n_cols"], old["dtype"]) != (self.n_walkers, self.n_cols, self.dtype.name):
+                raise ValueError("%s.bin holds %s walkers x %s columns of %s: cannot append %d x %d of %s"
+                                 % (base, old["n_walkers"], old["n_cols"], old["dtype"], self.n_walkers,
+                                    self.n_cols, self.dtype.name))
+            have = os.path.getsize(base + ".bin")
+            want = old["rows"] * self.n_walkers * self.n_cols * self.dtype.itemsize
+            if have < want:
+                raise ValueError("%s.bin is shorter than its sidecar says" % base)
+            self.rows = int(old["rows"])
+            self.meta = {**old, **self.meta}
+            self.fh = open(base + ".bin", "r+b")
+            self.fh.truncate(want)                      # drop a partial segment of an interrupted run
+            self.fh.seek(want)
+        else:
+            self.fh = open(base + ".bin", "wb")
+            if self.dtype == np.dtype("float32"):
+                if start is None:
+                    raise ValueError("float32 chains are differences: the starting points are needed")
+                st = np.ascontiguousarray(start, dtype=np.float64)
+                assert st.shape == (self.n_walkers, self.n_cols)
+                st.tofile(base + ".start.bin")
 
     def append(self, segment):
-        seg = np.ascontiguousarray(segment, dtype=np.float64)
+        seg = np.ascontiguousarray(segment, dtype=self.dtype)
         assert seg.shape[1:] == (self.n_walkers, self.n_cols)
         self.fh.write(seg.tobytes())
         self.rows += seg.shape[0]
@@ -123,15 +152,22 @@ class PackedChainWriter:
         self.fh.close()
         self.meta.update(extra)
         self.meta.update({"rows": self.rows, "n_walkers": self.n_walkers, "n_cols": self.n_cols,
-                          "dtype": "float64", "order": "[row][walker][column]"})
+                          "dtype": self.dtype.name, "order": "[row][walker][column]",
+                          "values": "differences from <base>.start.bin" if self.dtype == np.dtype("float32") else "absolute"})
         with open(self.base + ".json", "w") as fh:
             json.dump(self.meta, fh, indent=1)
 
 
 def read_packed(base):
+    """(chain [rows, walkers, columns] float64, meta) of a packed chain, whatever its storage type."""
     with open(base + ".json") as fh:
         meta = json.load(fh)
-    arr = np.fromfile(base + ".bin", dtype=np.float64).reshape(meta["rows"], meta["n_walkers"], meta["n_cols"])
+    shape = (meta["rows"], meta["n_walkers"], meta["n_cols"])
+    dt = np.dtype(meta.get("dtype", "float64"))
+    arr = np.fromfile(base + ".bin", dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    if dt == np.dtype("float32"):
+        start = np.fromfile(base + ".start.bin", dtype=np.float64).reshape(shape[1:])
+        arr = start[None] + arr.astype(np.float64)
     return arr, meta
 
 

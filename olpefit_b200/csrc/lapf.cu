@@ -262,7 +262,13 @@ struct RunArgs {
     uint32_t* tries;             // [W][P]
     uint32_t* accepts;           // [W][P]
     unsigned long long* exps;    // [W] exponentials actually evaluated (after far-field culling)
-    double* chain;               // [rows][W][P+1] or nullptr
+    void* chain;                 // [rows][W][P+1] double, or float (value - shift) when chain_f32; or nullptr
+    // separation / position-angle sketches of the recorded rows (apf_step3.py:255-256,283-291), or nullptr
+    uint32_t* sk_hist;           // [F][NB-1][2][sk_bins + 2]: underflow, bins, overflow
+    const double* sk_center;     // [F][NB-1][2]: separation (pixels), position angle (degrees) of bin sk_bins / 2
+    double* sk_mom;              // [W][NB-1][2][2]: per walker sum / sum of squares of (value - centre)
+    double sk_inv_sep, sk_inv_pa;   // 1 / bin width
+    int sk_bins, chain_f32;
     int64_t n_walkers;
     int64_t t0, n_updates;       // first update index, updates in this launch
     int64_t next_record;         // first count >= t0+1 at which a row is recorded
@@ -272,6 +278,34 @@ struct RunArgs {
     uint32_t log_mask;
     int thin, floor_index, n_items, cull, plain;
 };
+
+// One recorded row of one walker enters the sketches of its frame: for every companion the
+// separation sqrt(dx^2 + dy^2) in pixels and the position angle degrees(atan2(-dx, dy))
+// (apf_step3.py:255-256,283-291; 3-body: both pairs, 3body/apf_step3_3body.py:273-276,318-324)
+// relative to the frame's centre values, into fixed-width bins (integer atomics: order-independent)
+// and into the walker's own running sums (single writer: deterministic).
+template <int NB>
+__device__ __forceinline__ void record_sketch(const RunArgs& a, int wl, int frame, const double* __restrict__ xy) {
+    const double xs = xy[0], ys = xy[1];
+#pragma unroll
+    for (int o = 1; o < NB; ++o) {
+        const double dx = xy[2 * o] - xs, dy = xy[2 * o + 1] - ys;
+        const double val[2] = {sqrt(dx * dx + dy * dy), atan2(-dx, dy) * 57.29577951308232};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const size_t slot = ((size_t)frame * (NB - 1) + (o - 1)) * 2 + q;
+            double d = val[q] - a.sk_center[slot];
+            if (q == 1) d -= 360.0 * rint(d * (1.0 / 360.0));            // angles wrap
+            const double pos = floor(d * (q ? a.sk_inv_pa : a.sk_inv_sep)) + (double)(a.sk_bins / 2);
+            // nan goes to the overflow bin
+            const int bin = (pos >= 0.0) ? ((pos < (double)a.sk_bins) ? 1 + (int)pos : a.sk_bins + 1) : ((pos < 0.0) ? 0 : a.sk_bins + 1);
+            atomicAdd(&a.sk_hist[slot * (size_t)(a.sk_bins + 2) + bin], 1u);
+            double* m = a.sk_mom + (((size_t)wl * (NB - 1) + (o - 1)) * 2 + q) * 2;
+            atomicAdd(m, d);
+            atomicAdd(m + 1, d * d);
+        }
+    }
+}
 
 // One walker for n_updates updates.  TEAM = 1: one warp does everything.  TEAM > 1 (few walkers,
 // latency matters): TEAM warps run this function for the SAME walker in lock-step; each repeats the
@@ -395,10 +429,19 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
             if (lane <= P && tw == 0) {
                 const size_t mi = (size_t)wl * (P + 1) + lane;
                 const double v = (lane == P) ? chi_c : p;
-                if (a.chain) a.chain[((size_t)row * a.n_walkers + wl) * (P + 1) + lane] = v;
                 const double dl = v - a.shift[mi];
+                if (a.chain) {
+                    const size_t ci = ((size_t)row * a.n_walkers + wl) * (P + 1) + lane;
+                    if (a.chain_f32) static_cast<float*>(a.chain)[ci] = (float)dl; else static_cast<double*>(a.chain)[ci] = v;
+                }
                 atomicAdd(&a.moments[2 * mi], dl);                    // single writer: plain RED, in order
                 atomicAdd(&a.moments[2 * mi + 1], dl * dl);
+            }
+            if (a.sk_hist) {
+                double xy[2 * NB];
+#pragma unroll
+                for (int j = 0; j < 2 * NB; ++j) xy[j] = shfl_f64(p, j);
+                if (lane == 0 && tw == 0) record_sketch<NB>(a, wl, frame, xy);
             }
             ++row;
             next_rec += a.thin;   // (saturates harmlessly: a launch is shorter than 2^30)
@@ -552,10 +595,19 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
                 for (int j = 0; j <= P; ++j) {
                     const size_t mi = (size_t)wl * (P + 1) + j;
                     const double v = (j == P) ? chi_c : st[j];
-                    if (a.chain) a.chain[((size_t)row * a.n_walkers + wl) * (P + 1) + j] = v;
                     const double dl = v - a.shift[mi];
+                    if (a.chain) {
+                        const size_t ci = ((size_t)row * a.n_walkers + wl) * (P + 1) + j;
+                        if (a.chain_f32) static_cast<float*>(a.chain)[ci] = (float)dl; else static_cast<double*>(a.chain)[ci] = v;
+                    }
                     atomicAdd(&a.moments[2 * mi], dl);                    // single writer: plain RED, in order
                     atomicAdd(&a.moments[2 * mi + 1], dl * dl);
+                }
+                if (a.sk_hist) {
+                    double xy[2 * NB];
+#pragma unroll
+                    for (int j = 0; j < 2 * NB; ++j) xy[j] = st[j];
+                    record_sketch<NB>(a, wl, frame, xy);
                 }
             }
             ++row;
@@ -574,7 +626,11 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
     constexpr int TAB = Scratch<NB, NX, NY>::FLOATS;
     // stamps of up to 64 x 64 pixels also live in the TMEM pixel store (see tmem_fill_stamp)
     // (128 x 128: the weight plane only, the data plane is read from shared memory)
+#ifdef LAPF_EXP_NOTM   /* experiment only: pixel planes from shared memory */
+    constexpr int TM = 0;
+#else
     constexpr int TM = (Geo<NX>::PANELS == 1 && Rows<NY, 1>::HALVES == 1) ? 1 : 2;
+#endif
     constexpr uint32_t TM_COLS = TM == 1 ? 16 * (NY / Geo<NX>::RG) : 512;
     static_assert(TM_COLS >= 32 && TM_COLS <= 512 && (TM_COLS & (TM_COLS - 1)) == 0, "TMEM allocations are powers of two");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -764,6 +820,94 @@ __global__ void frame_prep_kernel(const float* __restrict__ frames, int F, int f
     weight_out[i] = w;
 }
 
+// Centre values of the sketches when the caller gives none: separation / position angle of the
+// starting point of the frame's first walker.
+__global__ void sketch_center_kernel(const double* __restrict__ shift, const int32_t* __restrict__ walker_of,
+                                     const int32_t* __restrict__ frame_start, int F, int P, int nbody,
+                                     double* __restrict__ center /*[F][nbody-1][2]*/) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * (nbody - 1)) return;
+    const int f = i / (nbody - 1), o = 1 + i % (nbody - 1);
+    double sep = 0.0, pa = 0.0;
+    if (frame_start[f + 1] > frame_start[f]) {
+        const double* x = shift + (size_t)walker_of[frame_start[f]] * (P + 1);
+        const double dx = x[2 * o] - x[0], dy = x[2 * o + 1] - x[1];
+        sep = sqrt(dx * dx + dy * dy);
+        pa = atan2(-dx, dy) * 57.29577951308232;
+    }
+    center[2 * i] = sep;
+    center[2 * i + 1] = pa;
+}
+
+// Per frame and sketch slot: centre, sum and sum of squares of (value - centre) over the frame's
+// walkers (fixed order) and the number of values -- mean and standard deviation without the chain.
+__global__ void sketch_reduce_kernel(const double* __restrict__ sk_mom, const double* __restrict__ center,
+                                     const int32_t* __restrict__ walker_of, const int32_t* __restrict__ frame_start,
+                                     int slots /*(nbody-1)*2*/, int64_t n_rows, double* __restrict__ out /*[F][slots][4]*/) {
+    const int f = blockIdx.x, q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q >= slots) return;
+    const int b = frame_start[f], e = frame_start[f + 1];
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = b + lane; i < e; i += 32) {
+        const double* m = sk_mom + ((size_t)walker_of[i] * slots + q) * 2;
+        s1 += m[0];
+        s2 += m[1];
+    }
+    s1 = warp_sum_f64(s1);
+    s2 = warp_sum_f64(s2);
+    if (lane == 0) {
+        double* o = out + ((size_t)f * slots + q) * 4;
+        o[0] = center[(size_t)f * slots + q];
+        o[1] = s1;
+        o[2] = s2;
+        o[3] = (double)(e - b) * (double)n_rows;
+    }
+}
+
+// sum w, sum w d, sum w d^2 over the pixels of each frame OUTSIDE its cut-out, with the weight map
+// of frame_prep_kernel (lapf_problem.outside): per (frame, row tile) partials in FP64, fixed order.
+__global__ void __launch_bounds__(256)
+outside_partial_kernel(const float* __restrict__ frames, int fy, int fx, const int32_t* __restrict__ cut, int ny, int nx,
+                       double satcut, double rn2, int rows_per_tile, double* __restrict__ partial /*[F][tiles][3]*/) {
+    const int f = blockIdx.y, tile = blockIdx.x;
+    const int cx = cut[2 * f], cy = cut[2 * f + 1];
+    const int r0 = tile * rows_per_tile, r1 = min(fy, r0 + rows_per_tile);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int r = r0; r < r1; ++r) {
+        const bool row_in = r >= cy && r < cy + ny;
+        const float* src = frames + ((size_t)f * fy + r) * fx;
+        for (int c = threadIdx.x; c < fx; c += blockDim.x) {
+            if (row_in && c >= cx && c < cx + nx) continue;
+            const float v = src[c];
+            if (isfinite(v) && !((double)v > satcut)) {
+                const double w = (double)(float)(1.0 / (rn2 + fabs((double)v)));
+                const double d = (double)v;
+                s0 += w;
+                s1 += w * d;
+                s2 += w * d * d;
+            }
+        }
+    }
+    __shared__ double red[8][3];
+    s0 = warp_sum_f64(s0); s1 = warp_sum_f64(s1); s2 = warp_sum_f64(s2);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s0; red[threadIdx.x >> 5][1] = s1; red[threadIdx.x >> 5][2] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i][threadIdx.x];
+        partial[((size_t)f * gridDim.x + tile) * 3 + threadIdx.x] = t;
+    }
+}
+
+__global__ void outside_reduce_kernel(const double* __restrict__ partial, int F, int tiles, double* __restrict__ out /*[F][3]*/) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * F) return;
+    const int f = i / 3, q = i % 3;
+    double t = 0.0;
+    for (int k = 0; k < tiles; ++k) t += partial[((size_t)f * tiles + k) * 3 + q];
+    out[i] = t;
+}
+
 // =============================================================================================
 // roofline micro-benchmarks
 // =============================================================================================
@@ -828,6 +972,15 @@ struct lapf_sampler {
     int32_t* item_first = nullptr;
     int32_t* item_count = nullptr;
     int32_t* cta_item = nullptr;   // batched kernel: first item of every CTA
+    // chain rows leave as double values or as float differences from the starting point
+    int chain_format = LAPF_CHAIN_F64;
+    // separation / position-angle sketches (lapf_sampler_sketch_enable)
+    int sk_bins = 0;
+    bool sk_auto_center = true;
+    double sk_sep_bin = 0.0, sk_pa_bin = 0.0;
+    uint32_t* sk_hist = nullptr;
+    double* sk_center = nullptr;
+    double* sk_mom = nullptr;
     int chunk = 0;                 // batched kernel: walkers per item at most (warps x walkers per warp)
     int launch_grid = 0;           // batched kernel: CTAs that have work
 };
@@ -1039,7 +1192,7 @@ static int launch_batch_dispatch(lapf_sampler* s, const RunArgs& a, cudaStream_t
 #define LAPF_DISPATCH_TEAM(FN, NB_, NX_, NW_, ...)                                          \
     do {                                                                                    \
         if (s->team == 4) return FN<NB_, NX_, NW_, 1, 4>(__VA_ARGS__);                      \
-        if (s->team == 16 && NX_ >= 64 && NW_ == 16) return FN<NB_, NX_, 16, 1, (NX_ >= 64 ? 16 : 4)>(__VA_ARGS__); \
+        if (s->team == 16 && NX_ >= 64) return FN<NB_, NX_, 16, 1, (NX_ >= 64 ? 16 : 4)>(__VA_ARGS__); \
     } while (0)
 
 #define LAPF_DISPATCH_GIBBS(FN, ...)                                                        \
@@ -1069,6 +1222,7 @@ static void free_sampler(lapf_sampler* s) {
     cudaFree(s->state); cudaFree(s->shift); cudaFree(s->moments); cudaFree(s->tries); cudaFree(s->accepts); cudaFree(s->exps);
     cudaFree(s->walker_of); cudaFree(s->frame_start); cudaFree(s->item_frame); cudaFree(s->item_first);
     cudaFree(s->item_count); cudaFree(s->cta_item);
+    cudaFree(s->sk_hist); cudaFree(s->sk_center); cudaFree(s->sk_mom);
     delete s;
 }
 
@@ -1214,13 +1368,26 @@ int lapf_sampler_reset(lapf_sampler* s, const double* init_params, uint64_t seed
     s->launches += 2;
     s->cfg.seed = seed;
     s->count = 0;
+    if (s->sk_hist) {
+        const int F = s->cfg.problem.n_frames, slots = 2 * (s->cfg.problem.nbody - 1);
+        CU(cudaMemsetAsync(s->sk_hist, 0, sizeof(uint32_t) * (size_t)F * slots * (s->sk_bins + 2), st));
+        CU(cudaMemsetAsync(s->sk_mom, 0, sizeof(double) * (size_t)W * slots * 2, st));
+        if (s->sk_auto_center) {
+            sketch_center_kernel<<<(F * (slots / 2) + 127) / 128, 128, 0, st>>>(s->shift, s->walker_of, s->frame_start, F, P,
+                                                                              s->cfg.problem.nbody, s->sk_center);
+            CU(cudaGetLastError());
+            s->launches++;
+        }
+    }
     return LAPF_OK;
 }
 
-// Checkpoint layout (device blob, 8-byte units): [count][seed] state shift moments(2x) exps tries accepts
+// Checkpoint layout (device blob, 8-byte units): [count][seed][jump widths x LAPF_MAX_PARAMS] state shift
+// moments(2x) exps tries accepts
+constexpr size_t kCkptHead = 8 * (2 + LAPF_MAX_PARAMS);
 static size_t checkpoint_bytes(const lapf_sampler* s) {
     const size_t W = (size_t)s->cfg.n_walkers, P = (size_t)s->P, nst = W * (P + 1);
-    return 16 + sizeof(double) * nst * 4 + sizeof(unsigned long long) * W + sizeof(uint32_t) * W * P * 2;
+    return kCkptHead + sizeof(double) * nst * 4 + sizeof(unsigned long long) * W + sizeof(uint32_t) * W * P * 2;
 }
 
 int64_t lapf_sampler_checkpoint_bytes(const lapf_sampler* s) {
@@ -1233,7 +1400,7 @@ static int checkpoint_copy(lapf_sampler* s, unsigned char* blob, bool save, cuda
     struct Part { void* dev; size_t bytes; } parts[] = {
         {s->state, sizeof(double) * nst}, {s->shift, sizeof(double) * nst}, {s->moments, sizeof(double) * nst * 2},
         {s->exps, sizeof(unsigned long long) * W}, {s->tries, sizeof(uint32_t) * W * P}, {s->accepts, sizeof(uint32_t) * W * P}};
-    size_t off = 16;
+    size_t off = kCkptHead;
     for (const Part& p : parts) {
         CU(cudaMemcpyAsync(save ? (void*)(blob + off) : p.dev, save ? p.dev : (const void*)(blob + off), p.bytes,
                            cudaMemcpyDeviceToDevice, st));
@@ -1246,8 +1413,9 @@ int lapf_sampler_save(lapf_sampler* s, void* blob, int64_t blob_bytes, void* str
     if (!s || !blob) return fail(LAPF_ERR_INVALID, "sampler/blob is NULL");
     if ((size_t)blob_bytes < checkpoint_bytes(s)) return fail(LAPF_ERR_INVALID, "checkpoint buffer too small");
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t head[2] = {s->count, (int64_t)s->cfg.seed};
-    CU(cudaMemcpyAsync(blob, head, 16, cudaMemcpyHostToDevice, st));
+    int64_t head[2 + LAPF_MAX_PARAMS] = {s->count, (int64_t)s->cfg.seed};
+    memcpy(head + 2, s->widths, sizeof(double) * LAPF_MAX_PARAMS);   // --adapt may have changed them
+    CU(cudaMemcpyAsync(blob, head, kCkptHead, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));   // `head` lives on this stack frame
     return checkpoint_copy(s, (unsigned char*)blob, true, st);
 }
@@ -1256,12 +1424,17 @@ int lapf_sampler_load(lapf_sampler* s, const void* blob, int64_t blob_bytes, voi
     if (!s || !blob) return fail(LAPF_ERR_INVALID, "sampler/blob is NULL");
     if ((size_t)blob_bytes < checkpoint_bytes(s)) return fail(LAPF_ERR_INVALID, "checkpoint buffer too small");
     cudaStream_t st = (cudaStream_t)stream;
-    int64_t head[2] = {0, 0};
-    CU(cudaMemcpyAsync(head, blob, 16, cudaMemcpyDeviceToHost, st));
+    int64_t head[2 + LAPF_MAX_PARAMS] = {0, 0};
+    CU(cudaMemcpyAsync(head, blob, kCkptHead, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (head[0] < 0) return fail(LAPF_ERR_INVALID, "corrupt checkpoint (count %lld)", (long long)head[0]);
+    double wd[LAPF_MAX_PARAMS];
+    memcpy(wd, head + 2, sizeof(wd));
+    bool ok = head[0] >= 0;
+    for (int i = 0; i < s->P; ++i) ok = ok && wd[i] >= 0.0 && std::isfinite(wd[i]);
+    if (!ok) return fail(LAPF_ERR_INVALID, "corrupt checkpoint (count %lld)", (long long)head[0]);
     s->count = head[0];
     s->cfg.seed = (uint64_t)head[1];
+    memcpy(s->widths, wd, sizeof(wd));
     return checkpoint_copy(s, (unsigned char*)const_cast<void*>(blob), false, st);
 }
 
@@ -1287,7 +1460,7 @@ int64_t lapf_sampler_rows_for(const lapf_sampler* s, int64_t n_updates) {
 int64_t lapf_sampler_count(const lapf_sampler* s) { return s ? s->count : fail(LAPF_ERR_INVALID, "sampler is NULL"); }
 int64_t lapf_sampler_launches(const lapf_sampler* s) { return s ? s->launches : fail(LAPF_ERR_INVALID, "sampler is NULL"); }
 
-int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int64_t rows_cap, void* stream) {
+int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, void* chain_out, int64_t rows_cap, void* stream) {
     if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
     if (n_updates < 0 || n_updates > ((int64_t)1 << 30))
         return fail(LAPF_ERR_INVALID, "n_updates must be in [0, 2^30] per launch");
@@ -1303,6 +1476,11 @@ int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, double* chain_out, int6
     a.state = s->state; a.shift = s->shift; a.moments = s->moments;
     a.tries = s->tries; a.accepts = s->accepts; a.exps = s->exps;
     a.chain = chain_out;
+    a.chain_f32 = s->chain_format == LAPF_CHAIN_F32_DELTA ? 1 : 0;
+    a.sk_hist = s->sk_hist; a.sk_center = s->sk_center; a.sk_mom = s->sk_mom;
+    a.sk_bins = s->sk_bins;
+    a.sk_inv_sep = s->sk_bins ? 1.0 / s->sk_sep_bin : 0.0;
+    a.sk_inv_pa = s->sk_bins ? 1.0 / s->sk_pa_bin : 0.0;
     a.n_walkers = s->cfg.n_walkers;
     a.t0 = s->count; a.n_updates = n_updates;
     a.next_record = next_record_after(s->count, s->cfg.burn_in, s->cfg.thin);
@@ -1355,6 +1533,93 @@ int lapf_sampler_stats(lapf_sampler* s, int64_t* totals_out, double* moments_out
         CU(cudaGetLastError());
         s->launches++;
     }
+    return LAPF_OK;
+}
+
+int lapf_sampler_set_chain_format(lapf_sampler* s, int32_t format) {
+    if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
+    if (format != LAPF_CHAIN_F64 && format != LAPF_CHAIN_F32_DELTA)
+        return fail(LAPF_ERR_INVALID, "unknown chain format %d", format);
+    s->chain_format = format;
+    return LAPF_OK;
+}
+
+int lapf_sampler_start(lapf_sampler* s, double* start_out, void* stream) {
+    if (!s || !start_out) return fail(LAPF_ERR_INVALID, "sampler/start_out is NULL");
+    CU(cudaMemcpyAsync(start_out, s->shift, sizeof(double) * (size_t)s->cfg.n_walkers * (s->P + 1), cudaMemcpyDeviceToDevice,
+                       (cudaStream_t)stream));
+    return LAPF_OK;
+}
+
+int lapf_sampler_sketch_enable(lapf_sampler* s, int32_t n_bins, double sep_bin, double pa_bin, const double* centers,
+                               void* stream) {
+    if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
+    if (n_bins < 2 || n_bins > (1 << 20) || (n_bins & 1) || !(sep_bin > 0.0) || !(pa_bin > 0.0))
+        return fail(LAPF_ERR_INVALID, "sketch needs an even n_bins in [2, 2^20] and positive bin widths");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = s->cfg.problem.n_frames, nbody = s->cfg.problem.nbody, slots = 2 * (nbody - 1);
+    const int64_t W = s->cfg.n_walkers;
+    CU(cudaStreamSynchronize(st));
+    cudaFree(s->sk_hist); cudaFree(s->sk_center); cudaFree(s->sk_mom);
+    s->sk_hist = nullptr; s->sk_center = nullptr; s->sk_mom = nullptr;
+    s->sk_bins = 0;
+    CU(cudaMalloc((void**)&s->sk_hist, sizeof(uint32_t) * (size_t)F * slots * (n_bins + 2)));
+    CU(cudaMalloc((void**)&s->sk_center, sizeof(double) * (size_t)F * slots));
+    CU(cudaMalloc((void**)&s->sk_mom, sizeof(double) * (size_t)W * slots * 2));
+    CU(cudaMemsetAsync(s->sk_hist, 0, sizeof(uint32_t) * (size_t)F * slots * (n_bins + 2), st));
+    CU(cudaMemsetAsync(s->sk_mom, 0, sizeof(double) * (size_t)W * slots * 2, st));
+    s->sk_auto_center = centers == nullptr;
+    if (centers) {
+        CU(cudaMemcpyAsync(s->sk_center, centers, sizeof(double) * (size_t)F * slots, cudaMemcpyDeviceToDevice, st));
+    } else {
+        sketch_center_kernel<<<(F * (nbody - 1) + 127) / 128, 128, 0, st>>>(s->shift, s->walker_of, s->frame_start, F, s->P,
+                                                                          nbody, s->sk_center);
+        CU(cudaGetLastError());
+        s->launches++;
+    }
+    s->sk_bins = n_bins;
+    s->sk_sep_bin = sep_bin;
+    s->sk_pa_bin = pa_bin;
+    return LAPF_OK;
+}
+
+int lapf_sampler_sketch(lapf_sampler* s, uint32_t* hist_out, double* summary_out, void* stream) {
+    if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
+    if (!s->sk_hist) return fail(LAPF_ERR_INVALID, "sketches are not enabled (lapf_sampler_sketch_enable)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = s->cfg.problem.n_frames, slots = 2 * (s->cfg.problem.nbody - 1);
+    if (hist_out)
+        CU(cudaMemcpyAsync(hist_out, s->sk_hist, sizeof(uint32_t) * (size_t)F * slots * (s->sk_bins + 2),
+                           cudaMemcpyDeviceToDevice, st));
+    if (summary_out) {
+        // rows recorded since the sketches were last zeroed = rows recorded so far (enable before the first run)
+        const int64_t n_rows = rows_upto(s->count, s->cfg.burn_in, s->cfg.thin);
+        sketch_reduce_kernel<<<F, 32 * slots, 0, st>>>(s->sk_mom, s->sk_center, s->walker_of, s->frame_start, slots, n_rows,
+                                                      summary_out);
+        CU(cudaGetLastError());
+        s->launches++;
+    }
+    return LAPF_OK;
+}
+
+int lapf_frame_outside(const float* frames, int32_t n_frames, int32_t fy, int32_t fx, const int32_t* cut, int32_t ny,
+                       int32_t nx, double satlevel, double readnoise, double* outside_out, void* stream) {
+    if (!frames || !cut || !outside_out || n_frames <= 0 || fy <= 0 || fx <= 0 || ny <= 0 || nx <= 0)
+        return fail(LAPF_ERR_INVALID, "bad arguments to lapf_frame_outside");
+    int rc = require_device();
+    if (rc) return rc;
+    keep_pool_memory();
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows_per_tile = 16, tiles = (fy + rows_per_tile - 1) / rows_per_tile;
+    if (n_frames > 65535) return fail(LAPF_ERR_INVALID, "lapf_frame_outside handles at most 65535 frames per call");
+    double* partial = nullptr;
+    CU(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)n_frames * tiles * 3, st));
+    outside_partial_kernel<<<dim3((unsigned)tiles, (unsigned)n_frames), 256, 0, st>>>(
+        frames, fy, fx, cut, ny, nx, 0.8 * satlevel, readnoise * readnoise, rows_per_tile, partial);
+    CU(cudaGetLastError());
+    outside_reduce_kernel<<<(3 * n_frames + 127) / 128, 128, 0, st>>>(partial, n_frames, tiles, outside_out);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(partial, st));
     return LAPF_OK;
 }
 

@@ -137,6 +137,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const float (&v)[16]) {
 // issue the load of 16 consecutive columns; the registers are valid only after tmem_ld16_wait
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t addr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+#ifdef LAPF_EXP_FUSED
+                 " tcgen05.wait::ld.sync.aligned;"
+#endif
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(addr));
@@ -393,6 +396,11 @@ struct Scratch {
 // selects): a quarter of the instructions and of the serialised MUFUs on the latency path of an
 // update.  (Whole-warp passes keep one block per lane: on 32-pixel stamps, the only case with lanes
 // to spare, the split was not faster.)
+#ifdef LAPF_EXP_BARSYNC
+#define LAPF_TABLE_SYNC() asm volatile("bar.warp.sync 0xffffffff;" ::: "memory")
+#else
+#define LAPF_TABLE_SYNC() __syncwarp()
+#endif
 template <int NB, int NX, int TR, int TEAM>
 __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Coef<NB>& cf, int lane, int row0, int tw) {
     using G = Geo<NX>;
@@ -400,8 +408,12 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
     constexpr int K = 2 * NB;
     constexpr int NQ = K / 2;                         // component pairs (narrow, wide) = objects
     constexpr int NBLK = TR / 2 / TEAM;
+#ifdef LAPF_EXP_SPLIT   /* experiment only: spread whole-warp tables over two lanes as well */
+    constexpr int SPLIT = NBLK >= 32 ? 1 : (NBLK >= 16 ? 2 : (TEAM == 1 ? 2 : 4));
+#else
     constexpr int SPLIT = (TEAM == 1 || NBLK >= 32) ? 1 : (NBLK >= 16 ? 2 : 4);
-    __syncwarp();   // readers of the previous table are done
+#endif
+    LAPF_TABLE_SYNC();   // readers of the previous table are done
 #pragma unroll
     for (int j0 = 0; j0 < NBLK * SPLIT; j0 += 32) {
         const int idx = j0 + lane;
@@ -442,7 +454,7 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
             }
         }
     }
-    __syncwarp();
+    LAPF_TABLE_SYNC();
 }
 
 // Far-field culling.  |A_k| 2^(q) <= |A_k| 2^(kappa dy^2) for every pixel of a row at distance dy
@@ -1100,11 +1112,15 @@ __device__ __forceinline__ Draw make_draw(uint64_t seed, uint64_t walker_id, uin
         make_uint2((uint32_t)seed, (uint32_t)walker_id));
     Draw d;
     d.k = (int)__umulhi(r.x, (uint32_t)nparam);
-    const double u1 = (double)((r.y >> 8) + 1u) * 0x1p-24;   // (0, 1]
-    const double u2 = (double)(r.z >> 8) * 0x1p-24;          // [0, 1)
+    // Box-Muller from two full 32-bit words: |z| reaches 6.66 sigma
+    const double u1 = ((double)r.y + 1.0) * 0x1p-32;         // (0, 1]
+    const double u2 = (double)r.z * 0x1p-32;                 // [0, 1)
     d.z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-    const double u = (double)(r.w >> 8) * 0x1p-24;           // [0, 1)
-    d.lnu = log(u);
+    // the accept/reject uniform carries 53 bits like numpy's rand() (apf_step2.py:143): the fourth
+    // word and the low 21 bits of the first, whose high bits picked the parameter
+    const uint64_t m = ((uint64_t)r.w << 21) | (uint64_t)(r.x & 0x1FFFFFu);
+    const double u = (double)m * 0x1p-53;                    // [0, 1)
+    d.lnu = log(u);                                          // -inf for u = 0 (probability 2^-53)
     return d;
 }
 

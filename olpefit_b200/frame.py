@@ -221,27 +221,92 @@ def prepare_domain(frames, header, size=None, cut=None, origin=None, nbody=2, fl
                                    data.data_ptr(), weight.data_ptr(), _stream_ptr(dev)))
     outside = None
     if whole_frame:
-        # full-array weight map through the same kernel, then all-minus-inside in FP64
-        zero = torch.zeros((nf, 2), dtype=torch.int32, device=dev)
-        d_all = torch.empty((nf, fy, fx), dtype=torch.float32, device=dev)
-        w_all = torch.empty_like(d_all)
-        _lib.check(lib.lapf_frame_prep(fr.data_ptr(), nf, fy, fx, zero.data_ptr(), fy, fx,
-                                       float(saturation_level(header)), float(read_noise(header)),
-                                       d_all.data_ptr(), w_all.data_ptr(), _stream_ptr(dev)))
-
-        def sums(d, w):
-            d64, w64 = d.double(), w.double()
-            return torch.stack([w64.sum(dim=(1, 2)), (w64 * d64).sum(dim=(1, 2)), (w64 * d64 * d64).sum(dim=(1, 2))], dim=1)
-
-        outside = sums(d_all, w_all) - sums(data, weight)
+        # sum w, sum w d, sum w d^2 over the pixels outside each cut-out: one pass over the frames on the
+        # device, FP64, fixed order (lapf_frame_outside)
+        outside = into.outside if (into is not None and into.outside is not None) else \
+            torch.empty((nf, 3), dtype=torch.float64, device=dev)
+        _lib.check(lib.lapf_frame_outside(fr.data_ptr(), nf, fy, fx, cut_t.data_ptr(), ny, nx,
+                                          float(saturation_level(header)), float(read_noise(header)),
+                                          outside.data_ptr(), _stream_ptr(dev)))
     if into is not None:
-        if outside is not None:
-            if into.outside is None:
-                raise ValueError("into was created without whole_frame=True")
-            into.outside.copy_(outside)
+        if outside is not None and into.outside is None:
+            raise ValueError("into was created without whole_frame=True")
         return into
     return PixelDomain(data, weight, (org_np + cut_np).astype(np.int32), nbody=nbody,
                        floor_index=floor_index, device=device, outside=outside)
+
+
+def stamp_cut(params, nbody, size, shape):
+    """(x, y) of the size x size cut-out centred on the objects, kept inside a frame of ``shape``."""
+    xs, ys = params[0:2 * nbody:2], params[1:2 * nbody:2]
+    ox = int(round(float(np.mean(xs)))) - size // 2
+    oy = int(round(float(np.mean(ys)))) - size // 2
+    ox = min(max(ox, 0), max(shape[1] - size, 0))
+    oy = min(max(oy, 0), max(shape[0] - size, 0))
+    return ox, oy
+
+
+def load_epochs(paths, start_fn, nbody=2, size=128, floor_index=None, device="cuda", whole_frame=True, chunk=32):
+    """Many epochs into one PixelDomain (the reference runs one process group per image,
+    apf_step2.py:154-161): every FITS frame is read, its starting point worked out by
+    ``start_fn(image, header, path) -> parameters[P]`` (frame coordinates), and a size x size cut-out
+    around the objects is masked, weighted and cut on the device (``lapf_frame_prep``), ``chunk``
+    frames at a time through one pinned staging buffer, so the full frames never pile up anywhere.
+    Returns (domain, parameters [F, P], cuts [F, 2], headers)."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.LapfError("no CUDA device: olpefit_b200 has no CPU path")
+    dev = torch.device(device)
+    nf = len(paths)
+    data = torch.empty((nf, size, size), dtype=torch.float32, device=dev)
+    weight = torch.empty_like(data)
+    outside = torch.empty((nf, 3), dtype=torch.float64, device=dev) if whole_frame else None
+    params, cuts, headers = [], [], []
+    stage = None
+    for f0 in range(0, nf, chunk):
+        f1 = min(nf, f0 + chunk)
+        scal = []
+        for f in range(f0, f1):
+            image, hdr = read_fits(paths[f])
+            if image.ndim != 2:
+                raise ValueError("%s: expected a 2-D image, got shape %s" % (paths[f], image.shape))
+            if stage is None:
+                fy, fx = image.shape
+                if fy < size or fx < size:
+                    raise ValueError("%s: frame %s is smaller than the %d-pixel stamp" % (paths[f], image.shape, size))
+                stage = torch.empty((chunk, fy, fx), dtype=torch.float32).pin_memory()
+                stage_d = torch.empty((chunk, fy, fx), dtype=torch.float32, device=dev)
+                done = torch.cuda.Event()
+            elif image.shape != (fy, fx):
+                raise ValueError("%s: frame shape %s differs from %s" % (paths[f], image.shape, (fy, fx)))
+            p = np.asarray(start_fn(image, hdr, paths[f]), dtype=np.float64)
+            params.append(p)
+            cuts.append(stamp_cut(p, nbody, size, image.shape))
+            headers.append(hdr)
+            scal.append((float(saturation_level(hdr)), float(read_noise(hdr))))
+            if f == f0:
+                done.synchronize()                      # the previous chunk has left the staging buffer
+            stage[f - f0].copy_(torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)))
+        n = f1 - f0
+        stage_d[:n].copy_(stage[:n], non_blocking=True)
+        done.record(torch.cuda.current_stream(dev))
+        cut_t = torch.as_tensor(np.asarray(cuts[f0:f1], dtype=np.int32)).to(dev)
+        g0 = 0
+        while g0 < n:                                   # runs of frames with equal header scalars share a launch
+            g1 = g0 + 1
+            while g1 < n and scal[g1] == scal[g0]:
+                g1 += 1
+            sat, rn = scal[g0]
+            _lib.check(lib.lapf_frame_prep(stage_d[g0:].data_ptr(), g1 - g0, fy, fx, cut_t[g0:].data_ptr(), size, size,
+                                           sat, rn, data[f0 + g0:].data_ptr(), weight[f0 + g0:].data_ptr(), _stream_ptr(dev)))
+            if whole_frame:
+                _lib.check(lib.lapf_frame_outside(stage_d[g0:].data_ptr(), g1 - g0, fy, fx, cut_t[g0:].data_ptr(), size,
+                                                  size, sat, rn, outside[f0 + g0:].data_ptr(), _stream_ptr(dev)))
+            g0 = g1
+    torch.cuda.synchronize(dev)
+    cuts = np.asarray(cuts, dtype=np.int32).reshape(nf, 2)
+    dom = PixelDomain(data, weight, cuts, nbody=nbody, floor_index=floor_index, device=device, outside=outside)
+    return dom, np.asarray(params), cuts, headers
 
 
 def initial_parameters(image, guess, nbody=2, origin=(0, 0)):

@@ -44,6 +44,8 @@ class GibbsSampler:
                           int(seed) & 0xFFFFFFFFFFFFFFFF, fo.data_ptr() if fo is not None else None,
                           p.data_ptr(), w_arr, int(burn_in), int(thin), int(team_warps))
         self.burn_in, self.thin = int(burn_in), int(thin)
+        self.chain_dtype = torch.float64
+        self._sketch = None
         handle = C.c_void_p()
         _lib.check(self.lib.lapf_sampler_create(C.byref(cfg), C.byref(handle), _stream_ptr(dev)))
         self._h = handle
@@ -100,6 +102,48 @@ class GibbsSampler:
             raise ValueError("widths must have %d entries" % self.nparam)
         _lib.check(self.lib.lapf_sampler_set_widths(self._h, (C.c_double * self.nparam)(*w_np.tolist())))
 
+    def set_chain_format(self, fmt: str):
+        """'f64': rows are the values themselves (default).  'f32delta': rows are float32 differences
+        from the walker's starting point (``start()``) -- half the bytes to drain, and exact to ~1e-7
+        of the distance travelled (see include/lapf.h)."""
+        code = {"f64": 0, "f32delta": 1}[fmt]
+        _lib.check(self.lib.lapf_sampler_set_chain_format(self._h, code))
+        self.chain_dtype = torch.float32 if code else torch.float64
+
+    def start(self):
+        """[W, P+1] float64 device tensor: every walker's starting point and its chi-square."""
+        out = torch.empty((self.n_walkers, self.nparam + 1), dtype=torch.float64, device=self.domain.device)
+        _lib.check(self.lib.lapf_sampler_start(self._h, out.data_ptr(), _stream_ptr(self.domain.device)))
+        return out
+
+    # -- separation / position angle without the chain (apf_step3.py:255-256,283-291,436-437) ---------
+    def enable_sketch(self, n_bins=8192, sep_bin=5e-4, pa_bin=2e-3, centers=None):
+        """From now on every recorded row enters per-frame histograms of separation (pixels) and
+        position angle (degrees) of each companion; call before the first ``run``.  ``centers``:
+        [F, nbody-1, 2] centre values (give every rank the same ones), default: the starting point
+        of each frame's first walker."""
+        dev = self.domain.device
+        c = None
+        if centers is not None:
+            c = centers if torch.is_tensor(centers) else torch.as_tensor(np.asarray(centers, dtype=np.float64))
+            c = c.to(dev, torch.float64).reshape(self.domain.n_frames, self.domain.nbody - 1, 2).contiguous()
+        _lib.check(self.lib.lapf_sampler_sketch_enable(self._h, int(n_bins), float(sep_bin), float(pa_bin),
+                                                       c.data_ptr() if c is not None else None, _stream_ptr(dev)))
+        self._sketch = (int(n_bins), float(sep_bin), float(pa_bin))
+
+    def sketch(self):
+        """dict(hist [F, nbody-1, 2, n_bins+2] int64, summary [F, nbody-1, 2, 4] float64 (centre, sum,
+        sum of squares of value - centre, count), n_bins, sep_bin, pa_bin) as device tensors."""
+        if self._sketch is None:
+            raise _lib.LapfError("sketches are not enabled")
+        dev = self.domain.device
+        n_bins, sep_bin, pa_bin = self._sketch
+        shape = (self.domain.n_frames, self.domain.nbody - 1, 2)
+        hist = torch.empty(shape + (n_bins + 2,), dtype=torch.int32, device=dev)      # uint32 counts
+        summ = torch.empty(shape + (4,), dtype=torch.float64, device=dev)
+        _lib.check(self.lib.lapf_sampler_sketch(self._h, hist.data_ptr(), summ.data_ptr(), _stream_ptr(dev)))
+        return {"hist": hist.long() & 0xFFFFFFFF, "summary": summ, "n_bins": n_bins, "sep_bin": sep_bin, "pa_bin": pa_bin}
+
     # -- the loop ------------------------------------------------------------------------
     @property
     def count(self) -> int:
@@ -114,16 +158,17 @@ class GibbsSampler:
 
     def run(self, n_updates: int, record=True, out=None):
         """Advance all walkers by ``n_updates`` updates.  Returns the chain rows recorded by this
-        call as a device tensor [rows, n_walkers, P+1] float64 (None when record is False)."""
+        call as a device tensor [rows, n_walkers, P+1] (float64, or float32 differences from
+        ``start()`` after ``set_chain_format('f32delta')``; None when record is False)."""
         rows = self.rows_for(n_updates)
         chain = None
         if record:
             if out is not None:
-                if out.dtype != torch.float64 or out.numel() < rows * self.n_walkers * (self.nparam + 1):
-                    raise ValueError("out is too small for %d rows" % rows)
+                if out.dtype != self.chain_dtype or out.numel() < rows * self.n_walkers * (self.nparam + 1):
+                    raise ValueError("out must be %s and hold %d rows" % (self.chain_dtype, rows))
                 chain = out
             else:
-                chain = torch.empty((rows, self.n_walkers, self.nparam + 1), dtype=torch.float64,
+                chain = torch.empty((rows, self.n_walkers, self.nparam + 1), dtype=self.chain_dtype,
                                     device=self.domain.device)
         _lib.check(self.lib.lapf_sampler_run(self._h, int(n_updates),
                                              chain.data_ptr() if chain is not None and rows > 0 else None,
@@ -176,8 +221,8 @@ class ChainStreamer:
         dev = sampler.domain.device
         cap_rows = max(1, -(-int(max_updates) // sampler.thin) + 1)
         shape = (cap_rows, sampler.n_walkers, sampler.nparam + 1)
-        self.dev = [torch.empty(shape, dtype=torch.float64, device=dev) for _ in range(2)]
-        self.host = [torch.empty(shape, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.dev = [torch.empty(shape, dtype=sampler.chain_dtype, device=dev) for _ in range(2)]
+        self.host = [torch.empty(shape, dtype=sampler.chain_dtype).pin_memory() for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.done = [torch.cuda.Event(), torch.cuda.Event()]
         self.pending = None          # (buffer index, rows)
@@ -201,7 +246,7 @@ class ChainStreamer:
         chain = s.run(n_updates, out=self.dev[i])
         rows = int(chain.shape[0])
         if rows:
-            nbytes = rows * s.n_walkers * (s.nparam + 1) * 8
+            nbytes = rows * s.n_walkers * (s.nparam + 1) * self.dev[i].element_size()
             _lib.check(s.lib.lapf_chain_drain(self.dev[i].data_ptr(), self.host[i].data_ptr(), nbytes,
                                               compute.cuda_stream, self.copy_stream.cuda_stream))
         self.done[i].record(self.copy_stream)

@@ -313,7 +313,7 @@ def philox4x32_10(counter, key):
 def device_draws(seed, walker, t, nparam):
     """The (index, standard normal, uniform) triple the CUDA sampler uses for update ``t``.
 
-    Stream definition (shared with olpefit_b200/csrc/lapf_rng.cuh): key = (seed low 32 bits,
+    Stream definition (shared with make_draw in olpefit_b200/csrc/lapf_device.cuh): key = (seed low 32 bits,
     walker id); counter = (t low, t high, seed high 32 bits, 'LAPF').  Draw order follows the
     reference: index (apf_step2.py:302), normal (:64/:68), uniform (:143).
     """
@@ -322,10 +322,12 @@ def device_draws(seed, walker, t, nparam):
         (t & 0xFFFFFFFF, (t >> 32) & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, PHILOX_TAG),
         (seed & 0xFFFFFFFF, walker & 0xFFFFFFFF))
     k = (r0 * nparam) >> 32
-    u1 = ((r1 >> 8) + 1) * 2.0 ** -24          # (0, 1]
-    u2 = (r2 >> 8) * 2.0 ** -24                # [0, 1)
+    u1 = (r1 + 1) * 2.0 ** -32                 # (0, 1]: Box-Muller from two full words
+    u2 = r2 * 2.0 ** -32                       # [0, 1)
     z = math.sqrt(-2.0 * math.log(u1)) * math.cos(2.0 * math.pi * u2)
-    u = (r3 >> 8) * 2.0 ** -24                 # [0, 1)
+    # 53-bit uniform like numpy's rand() (apf_step2.py:143): the fourth word and the low 21 bits
+    # of the first (its high bits picked the parameter)
+    u = ((r3 << 21) | (r0 & 0x1FFFFF)) * 2.0 ** -53          # [0, 1)
     return k, z, u
 
 

@@ -97,3 +97,85 @@ def test_checkpoint_resume_and_adapt_flags(tmp_path):
     assert cli.main_step2([path_c, "--accept-min", "40", "--adapt", "--walkers", "8", "--burn-in", "600",
                            "--seed", "21", "--stamp", "32", "--quiet"]) == 0
     assert np.genfromtxt(os.path.join(out_c, "0_finalarray_mpi.csv"), delimiter=",").shape[1] == 17
+
+
+def test_three_body_entry_point_with_all_defaults(tmp_path):
+    """3body/apf_step2_3body.py IMAGE with nothing but the stop rule shortened: 24 walkers, 128-pixel
+    stamp, whole-frame domain, automatic team size (16 warps per walker on a 3-body 128-pixel stamp)."""
+    from olpefit_b200 import chains, cli
+    path, out, _ = _write_case(tmp_path, 3)
+    assert cli.main_step2_3body([path, "--accept-min", "6", "--seed", "4", "--quiet"]) == 0
+    cols, npos = chains.ingest(out, 24)
+    assert npos == 6 and cols.shape[0] == 20 and cols.shape[2] == 24 and np.all(np.isfinite(cols))
+    assert os.path.exists(os.path.join(out, "step2_summary.json"))
+
+
+def test_many_epochs_in_one_run_and_device_side_summary(tmp_path):
+    """--frames: several epochs, each with its own step-1 file and results directory, advance in one
+    batched sampler; step2_summary.json per epoch comes from statistics reduced on the device and
+    agrees with the chain files; --no-chains writes the summary alone."""
+    import json
+    from olpefit_b200 import chains, cli, frame, synth
+    paths, outs = [], []
+    for f in range(3):
+        d = tmp_path / ("epoch%d" % f)
+        d.mkdir()
+        img, _ = synth.make_frame(f, 2)
+        p = str(d / ("N2.2009053%d.2996%d.LDIF.fits" % (f, f)))
+        frame.write_fits(p, img, synth.HEADER)
+        guess = synth.step1_guess(img, 2, sky_xy=(100, 120))
+        with open(chains.initial_guess_path(p), "w") as fh:
+            fh.write(" ".join(str(v) for v in guess) + "\n")
+        paths.append(p)
+        outs.append(chains.results_dir(p))
+    lst = tmp_path / "frames.txt"
+    lst.write_text("# epochs of one target\n" + "\n".join(paths[1:]) + "\n")
+    args = [paths[0], "--frames", str(lst), "--walkers", "6", "--accept-min", "40", "--burn-in", "300", "--seed", "9",
+            "--stamp", "32", "--domain", "stamp", "--thin", "2", "--quiet"]
+    assert cli.main_step2(args) == 0
+    for f in range(3):
+        cols, npos = chains.ingest(outs[f], 6)
+        assert npos == 4 and cols.shape[2] == 6 and np.all(np.isfinite(cols))
+        summ = json.load(open(os.path.join(outs[f], "step2_summary.json")))
+        sep, pa = chains.separation_pa(cols[0], cols[1], cols[2], cols[3])
+        s = summ["sep_pa_companion"]
+        assert s["rows"] == sep.size
+        assert s["sep_mas"]["median"] == pytest.approx(np.median(sep), abs=0.011)      # one 5e-4 pixel bin, in mas
+        assert s["sep_mas"]["std"] == pytest.approx(np.std(sep), rel=1e-6)
+        assert s["pa_deg"]["median"] == pytest.approx(np.median(pa), abs=4.1e-3)
+        assert s["pa_deg"]["mean"] == pytest.approx(np.mean(pa), abs=1e-9)
+        assert len(summ["gelman_rubin"]) == 16
+        gr = [chains.gelman_rubin(cols[j])[1] for j in range(4)]
+        np.testing.assert_allclose(summ["gelman_rubin"][:4], gr, rtol=1e-6)
+    # the epochs differ (the companion drifts), and so do their chains
+    a = np.genfromtxt(os.path.join(outs[0], "0_finalarray_mpi.csv"), delimiter=",")
+    b = np.genfromtxt(os.path.join(outs[2], "0_finalarray_mpi.csv"), delimiter=",")
+    assert a.shape == b.shape and not np.array_equal(a[1:], b[1:])
+    # statistics only: same summary, no chain files touched
+    for o in outs:
+        for w in range(6):
+            os.unlink(os.path.join(o, "%d_finalarray_mpi.csv" % w))
+    before = [json.load(open(os.path.join(o, "step2_summary.json"))) for o in outs]
+    assert cli.main_step2(args + ["--no-chains"]) == 0
+    for f in range(3):
+        assert not os.path.exists(os.path.join(outs[f], "0_finalarray_mpi.csv"))
+        assert json.load(open(os.path.join(outs[f], "step2_summary.json"))) == before[f]
+
+
+def test_packed_float32_chain_and_its_resume(tmp_path):
+    """--format bin --chain-dtype f32, interrupted and resumed: the packed file of the two parts
+    equals the packed file of the uninterrupted run (--resume used to truncate it)."""
+    from olpefit_b200 import chains, cli
+    common = ["--walkers", "5", "--burn-in", "0", "--seed", "33", "--stamp", "32", "--segment", "64", "--format", "bin",
+              "--chain-dtype", "f32", "--quiet"]
+    path_a, out_a, _ = _write_case(tmp_path, 2, tag="_whole")
+    assert cli.main_step2([path_a, "--accept-min", "20"] + common) == 0
+    whole, meta = chains.read_packed(os.path.join(out_a, "chains_rank0"))
+    assert meta["dtype"] == "float32" and whole.shape[1:] == (5, 17)
+    path_b, out_b, _ = _write_case(tmp_path, 2, tag="_parts")
+    assert cli.main_step2([path_b, "--accept-min", "8", "--checkpoint"] + common) == 0
+    part, _ = chains.read_packed(os.path.join(out_b, "chains_rank0"))
+    assert 0 < part.shape[0] < whole.shape[0]
+    assert cli.main_step2([path_b, "--accept-min", "20", "--resume"] + common) == 0
+    both, meta_b = chains.read_packed(os.path.join(out_b, "chains_rank0"))
+    assert both.shape == whole.shape and np.array_equal(both, whole) and meta_b["count"] == meta["count"]

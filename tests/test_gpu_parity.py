@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the numpy oracle and the
 reference-executed golden vectors.  Tolerance for the pointwise tests is the one BASELINE.json
 states: 1e-5 relative (FP32 device arithmetic vs the reference's FP64)."""
+import math
 import os
 
 import numpy as np
@@ -394,30 +395,97 @@ def test_sampler_on_whole_frame_domain_replays_full_frame_oracle(gpu):
     assert res.accepts.sum() > 5
 
 
-def test_full_size_batch_state_is_consistent_with_k1(gpu):
-    """BASELINE configs[2] at full size (65,536 walkers x 100 epochs): after a run, the chi-square
-    every walker carries equals the stateless operator applied to its parameters -- bit for bit --
-    every update was counted once, and the batch statistics add up."""
+# walkers per CTA item of the batched kernel (warps x walkers per warp, LAPF_DISPATCH_BATCH in lapf.cu)
+BATCH_CHUNK = {(2, 32): 512, (2, 64): 512, (2, 128): 192, (3, 32): 512, (3, 64): 512, (3, 128): 144}
+
+
+@pytest.mark.parametrize("nbody,size,walkers,frames,n_upd", [
+    (2, 64, 65536, 100, 48),                       # BASELINE configs[2] at full size
+    (2, 32, 148 * (2 * 512 + 37), 5, 32),          # every CTA: two full items (32 walkers per warp) + a ragged one
+    (3, 32, 148 * (2 * 512 + 37), 5, 32),
+    (3, 64, 148 * (512 + 37), 3, 32),              # config 4's kernel, full warps
+    (2, 128, 148 * (192 + 29), 3, 16),             # TMEM holds the weight plane only (TM = 2), 16 walkers per warp
+    (3, 128, 148 * (144 + 29), 3, 16),             # 12 walkers per warp
+])
+def test_full_size_batch_state_is_consistent_with_k1(gpu, nbody, size, walkers, frames, n_upd):
+    """The batched kernel at the occupancy the benchmark times (many walkers per warp, coefficient
+    images in shared memory, TMEM pixel store), every shape: after a run, the chi-square every
+    walker carries equals the stateless operator K1 applied to its parameters -- bit for bit --
+    (apf_step2.py:314-327: a walker's chi-square is that of its vector), every update was counted
+    once, and the batch statistics add up."""
     torch = gpu["torch"]
     synth = gpu["synth"]
-    W, F, S = 65536, 100, 64
-    stamps, origins = synth.make_stamps(F, S)
-    dom = gpu["frame"].prepare_domain(stamps, HEADER, origin=origins, nbody=2)
+    W, F, S = walkers, frames, size
+    P = 3 * nbody + 10
+    assert W >= 148 * BATCH_CHUNK[(nbody, size)] or W == 65536
+    stamps, origins = synth.make_stamps(F, S, nbody)
+    dom = gpu["frame"].prepare_domain(stamps, HEADER, origin=origins, nbody=nbody)
     frame_of = (np.arange(W) % F).astype(np.int32)
-    p_frame = np.array([synth.truth_parameters(2, f) for f in range(F)])
-    with gpu["sampler"].GibbsSampler(dom, p_frame[frame_of], frame_of, seed=31, burn_in=0, thin=16) as s:
-        chain = s.run(48)
+    p_frame = np.array([synth.truth_parameters(nbody, f) for f in range(F)])
+    thin = 16
+    with gpu["sampler"].GibbsSampler(dom, p_frame[frame_of], frame_of, seed=31, burn_in=0, thin=thin) as s:
+        chain = s.run(n_upd)
         st, tries, acc = s.state()
         stats = s.stats()
-    assert chain.shape == (3, W, 17)
+    assert chain.shape == (n_upd // thin, W, P + 1)
     assert torch.equal(chain[-1], st)                                     # last recorded row = final state
-    _, chi = dom.model_chi2(st[:, :16], frame_of=frame_of)
-    assert torch.equal(chi, st[:, 16])                                    # K1 == K2, bitwise
-    assert bool((tries.sum(dim=1) == 48).all()) and bool((acc <= tries).all())
-    assert int(stats["tries"].sum()) == 48 * W
+    _, chi = dom.model_chi2(st[:, :P], frame_of=frame_of)
+    assert torch.equal(chi, st[:, P])                                     # K1 == K2, bitwise
+    assert bool((tries.sum(dim=1) == n_upd).all()) and bool((acc <= tries).all())
+    assert int(stats["tries"].sum()) == n_upd * W
+    assert 0.05 < float(acc.sum()) / float(tries.sum()) < 0.9             # chains move (a wrong chi-square freezes them)
     assert stats["walkers_per_frame"].cpu().numpy().tolist() == np.bincount(frame_of, minlength=F).tolist()
     # chi-square per pixel of chains started at the in-model truth stays of order one
-    assert 0.8 < float(st[:, 16].median()) / (S * S) < 1.3
+    assert 0.8 < float(st[:, P].median()) / (S * S) < 1.3
+
+
+@pytest.mark.parametrize("nbody,size,walkers", [(2, 64, 600), (3, 64, 600), (2, 32, 600), (3, 32, 600),
+                                                (2, 128, 230), (3, 128, 170)])
+def test_dense_warps_replay_oracle_stream(gpu, nbody, size, walkers):
+    """The oracle replay of test_sampler_replays_oracle_stream with MANY walkers per warp (more
+    than one CTA item of one frame: full lanes, the lane == i pick-up of the passes, a ragged second
+    item).  Walkers from different warps and lanes are replayed by the float64 oracle on the same
+    Philox stream; the device chain must follow update by update."""
+    lay = orc.layout_for(nbody)
+    dom, stamps, origins, p0 = _sampler_setup(gpu, nbody, size)
+    assert walkers > BATCH_CHUNK[(nbody, size)]
+    n_upd, seed = 160, 4321
+    init = np.tile(p0, (walkers, 1))
+    with gpu["sampler"].GibbsSampler(dom, init, seed=seed, burn_in=0, thin=1, id_base=11, id_stride=2) as s:
+        chain = s.run(n_upd).cpu().numpy()
+        st, tries, accepts = (t.cpu().numpy() for t in s.state())
+    assert np.all(tries.sum(axis=1) == n_upd)
+    img = stamps[0].astype(np.float64)
+    w = orc.weight_map(img, HEADER)
+    chunk = BATCH_CHUNK[(nbody, size)]
+    picks = sorted({0, 1, 15, 16, 17, chunk // 2 + 3, chunk - 1, chunk, chunk + 5, walkers - 1})
+    early = 0
+    for wi in picks:
+        gid = 11 + 2 * wi
+        stream = orc.PhiloxStream(seed, gid, lay.nparam)
+        res = orc.run_chain(img, w, lay, p0, stream, origin=tuple(origins[0]), n_updates=n_upd, burn_in=0,
+                            record_trace=True)
+        ref = res.rows[1:]
+        dev = chain[:, wi, :]
+        same = np.all(np.isclose(dev[:, :-1], ref[:, :-1], rtol=1e-9, atol=1e-12), axis=1)
+        first_bad = int(np.argmin(same)) if not same.all() else n_upd
+        np.testing.assert_allclose(dev[:first_bad, -1], ref[:first_bad, -1], rtol=RTOL)
+        if first_bad == n_upd:
+            assert np.array_equal(tries[wi], res.tries) and np.array_equal(accepts[wi], res.accepts)
+            continue
+        # the chains part at update first_bad: legitimate only if FP32 rounding of chi-square (within
+        # the stated 1e-5) can flip that decision, i.e. the float64 margin of the accept rule is tiny
+        k, new, chi_t, ok = res.trace[first_bad]
+        if first_bad > 0:
+            chi_c = ref[first_bad - 1, -1]
+        else:
+            chi_c = orc.chi_squared_weighted(img, orc.model_image(p0, lay, size, size, origin=tuple(origins[0])), w)
+        u = orc.device_draws(seed, gid, first_bad, lay.nparam)[2]
+        margin = abs(math.log(u) + 0.5 * (chi_t - chi_c))
+        assert margin <= 0.5 * RTOL * (abs(chi_t) + abs(chi_c)), (
+            "walker %d left the oracle chain at update %d with a clear decision (margin %.3g)" % (wi, first_bad, margin))
+        early += first_bad < 80
+    assert early <= 2, "%d of %d replayed walkers met a borderline decision before update 80" % (early, len(picks))
 
 
 @pytest.mark.parametrize("nbody,size", [(2, 64), (2, 128), (3, 128)])
@@ -509,6 +577,15 @@ def test_checkpoint_resume_is_exact_and_widths_can_be_retuned(gpu):
         s.run(200, record=False)
         acc1 = float(s.stats()["accepts"].sum()) - acc0
     assert acc1 < 0.8 * acc0
+    # the checkpoint carries the jump widths: a chain tuned during burn-in continues with the tuned scale
+    with gpu["sampler"].GibbsSampler(dom, init, fo, seed=4) as a:
+        a.set_widths(w0 * 3.0)
+        a.run(30, record=False)
+        blob = a.save().clone()
+        want = a.run(40)
+    with gpu["sampler"].GibbsSampler(dom, init, fo, seed=4) as b:            # default widths until load()
+        b.load(blob)
+        assert torch.equal(b.run(40), want)
     with pytest.raises(Exception):
         s2 = gpu["sampler"].GibbsSampler(dom, init, fo, seed=4)
         try:
@@ -716,3 +793,106 @@ def test_stream_of_epochs_reuses_domain_and_sampler(gpu):
         assert np.array_equal(got[b], fresh[b][0]), "batch %d" % b
     for x, y in zip(state, fresh[2][1]):
         assert np.array_equal(x, y)
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: statistics without the chain, compact chain rows, outside sums
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nbody,team", [(2, 1), (3, 1), (2, 4)])
+def test_device_sketches_match_the_recorded_chain(gpu, nbody, team):
+    """lapf_sampler_sketch: separation / position-angle histograms and sums accumulated in the
+    record step equal what numpy gets from the chain rows the same run recorded
+    (apf_step3.py:255-256,283-291,436-437) -- counts exactly, quantiles to one bin width."""
+    torch = gpu["torch"]
+    from olpefit_b200 import stats
+    dom, stamps, origins, p0 = _sampler_setup(gpu, nbody, 32, n_frames=3)
+    walkers = 50
+    frame_of = (np.arange(walkers) % 3).astype(np.int32)
+    init = np.tile(p0, (walkers, 1))
+    n_bins, sep_bin, pa_bin = 1024, 1e-3, 5e-3
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, seed=8, burn_in=20, thin=3, team_warps=team) as s:
+        s.enable_sketch(n_bins=n_bins, sep_bin=sep_bin, pa_bin=pa_bin)
+        chain = torch.cat([s.run(100), s.run(140)], dim=0).cpu().numpy()
+        sk = s.sketch()
+    hist, summ = sk["hist"].cpu().numpy(), sk["summary"].cpu().numpy()
+    res = {k: v.cpu().numpy() for k, v in stats.sketch_summary(sk, pixscale=1.0).items()}
+    rows = chain.shape[0]
+    for f in range(3):
+        sel = frame_of == f
+        for o in range(1, nbody):
+            dx = chain[:, sel, 2 * o] - chain[:, sel, 0]
+            dy = chain[:, sel, 2 * o + 1] - chain[:, sel, 1]
+            for q, vals in enumerate((np.sqrt(dx * dx + dy * dy), np.degrees(np.arctan2(-dx, dy)))):
+                width = (sep_bin, pa_bin)[q]
+                c = summ[f, o - 1, q, 0]
+                assert summ[f, o - 1, q, 3] == rows * sel.sum() == hist[f, o - 1, q].sum()
+                pos = np.floor((vals - c) / width) + n_bins // 2
+                b = np.where(pos < 0, 0, np.where(pos >= n_bins, n_bins + 1, pos + 1)).astype(int)
+                ref_hist = np.bincount(b.ravel(), minlength=n_bins + 2)
+                # a value within rounding of a bin edge may fall on either side
+                assert np.abs(hist[f, o - 1, q] - ref_hist).sum() <= 4
+                assert summ[f, o - 1, q, 1] == pytest.approx((vals - c).sum(), rel=1e-9, abs=1e-9)
+                assert summ[f, o - 1, q, 2] == pytest.approx(((vals - c) ** 2).sum(), rel=1e-9)
+                qs = res["sep_q" if q == 0 else "pa_q"][f, o - 1]
+                assert np.max(np.abs(qs - np.percentile(vals, [15.865, 50.0, 84.135]))) <= width
+                assert res["sep_std" if q == 0 else "pa_std"][f, o - 1] == pytest.approx(vals.std(), rel=1e-6)
+    # reset zeroes the sketches
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, seed=8, thin=5) as s:
+        s.enable_sketch(n_bins=64, sep_bin=0.01, pa_bin=0.05)
+        s.run(50, record=False)
+        assert int(s.sketch()["hist"].sum()) == 10 * walkers * 2 * (nbody - 1)
+        s.reset(init, seed=9)
+        assert int(s.sketch()["hist"].sum()) == 0
+
+
+def test_float32_difference_rows_equal_the_float64_rows(gpu):
+    """LAPF_CHAIN_F32_DELTA: the same run, rows leaving as float32 differences from the starting
+    point: exactly float32(row - start), through run() and through the ChainStreamer."""
+    torch = gpu["torch"]
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 32, n_frames=2)
+    walkers = 600
+    frame_of = (np.arange(walkers) % 2).astype(np.int32)
+    init = np.tile(p0, (walkers, 1))
+    init[:, 0:4] += np.random.default_rng(1).normal(0, 0.02, (walkers, 4))
+    kw = dict(seed=17, burn_in=0, thin=2)
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, **kw) as a:
+        full = a.run(40)
+        start = a.start()
+    assert torch.equal(start[:, :16], torch.as_tensor(init, device=start.device))
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, **kw) as b:
+        b.set_chain_format("f32delta")
+        small = b.run(40)
+        assert small.dtype == torch.float32 and small.shape == full.shape
+        assert torch.equal(small, (full - start[None]).float())
+        streamer = gpu["sampler"].ChainStreamer(b, 20)
+        assert streamer.run(20) is None
+        seg = streamer.finish()
+        assert seg.dtype == np.float32 and seg.shape == (10, walkers, 17)
+    with gpu["sampler"].GibbsSampler(dom, init, frame_of, **kw) as c:
+        more = c.run(60)[20:]
+    assert np.array_equal(seg, (more - start[None]).float().cpu().numpy())
+    # positions survive to ~1e-9 of a pixel although they travel in 32 bits
+    back = start[None] + small.double()
+    assert float((back[..., :4] - full[..., :4]).abs().max()) < 1e-8
+
+
+def test_outside_sums_kernel_matches_float64_numpy(gpu):
+    """lapf_frame_outside (lapf_problem.outside): sum w, sum w d, sum w d^2 over the pixels outside
+    the cut-out with the device weight map, against numpy in float64."""
+    synth, frame = gpu["synth"], gpu["frame"]
+    imgs = np.stack([synth.make_frame(f, 2)[0] for f in range(2)])
+    imgs[1, 200:210, 300:310] = 30000.0                       # saturated pixels far from the objects: masked
+    imgs[0, 5, 7] = np.nan                                    # a dead pixel: no weight
+    cuts = np.array([[450, 448], [460, 470]], dtype=np.int32)
+    dom = frame.prepare_domain(imgs, HEADER, size=128, cut=cuts, whole_frame=True)
+    got = dom.outside.cpu().numpy()
+    sat, rn = frame.saturation_level(HEADER), frame.read_noise(HEADER)
+    for f in range(2):
+        v = imgs[f].astype(np.float64)
+        ok = np.isfinite(v) & ~(v > 0.8 * sat)
+        w = np.where(ok, (1.0 / (rn * rn + np.abs(np.where(ok, v, 0.0)))).astype(np.float32).astype(np.float64), 0.0)
+        d = np.where(ok, v, 0.0)
+        inside = np.zeros_like(ok)
+        inside[cuts[f, 1]:cuts[f, 1] + 128, cuts[f, 0]:cuts[f, 0] + 128] = True
+        w = np.where(inside, 0.0, w)
+        np.testing.assert_allclose(got[f], [w.sum(), (w * d).sum(), (w * d * d).sum()], rtol=1e-12)

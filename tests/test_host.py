@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.lapf_abi_version() == 1
+    assert lib.lapf_abi_version() == 2
 
 
 def test_tables_served_by_library_match_reference_tables(lib):
@@ -252,3 +252,58 @@ def test_automatic_step1_writes_the_reference_file(tmp_path):
     # the numbers feed step 2's starting point exactly like the reference's file does
     p = frame.initial_parameters(img, g, 2)
     assert p.shape == (16,) and p[6] == img[int(g[1] - 1), int(g[0] - 1)]
+
+
+def test_packed_chain_float32_differences_and_resume(tmp_path):
+    """--format bin --chain-dtype f32 stores float32 differences from the starting points; a resumed
+    run appends to the same file instead of truncating it (chains.PackedChainWriter)."""
+    from olpefit_b200 import chains
+    rng = np.random.default_rng(3)
+    start = np.array([[512.3, 511.7, 15000.0, 6.4, 1040.5]] * 4) + rng.normal(0, 1e-3, (4, 5))
+    full = start[None] + rng.normal(0, 3e-3, (9, 4, 5)) * np.array([1, 1, 100.0, 0.01, 1.0])
+    delta = (full - start[None]).astype(np.float32)
+    base = str(tmp_path / "chains_rank0")
+    w = chains.PackedChainWriter(base, 4, 5, {"seed": 1}, dtype="float32", start=start)
+    w.append(delta[:5])
+    w.close(count=5)
+    with open(base + ".bin", "ab") as fh:                       # a torn segment of an interrupted run
+        fh.write(b"\0" * 13)
+    w = chains.PackedChainWriter(base, 4, 5, dtype="float32", resume=True)
+    assert w.rows == 5
+    w.append(delta[5:])
+    w.close(count=9)
+    arr, meta = chains.read_packed(base)
+    assert arr.shape == (9, 4, 5) and meta["rows"] == 9 and meta["count"] == 9 and meta["seed"] == 1
+    assert np.array_equal(arr, start[None] + delta.astype(np.float64))
+    # positions keep 1e-9 absolute although they are stored in 32 bits
+    assert np.max(np.abs(arr[..., 0] - full[..., 0])) < 2e-9
+    with pytest.raises(ValueError):
+        chains.PackedChainWriter(base, 3, 5, dtype="float32", resume=True)
+    # float64 resume
+    base2 = str(tmp_path / "c64")
+    w = chains.PackedChainWriter(base2, 4, 5)
+    w.append(full[:2]); w.close()
+    w = chains.PackedChainWriter(base2, 4, 5, resume=True)
+    w.append(full[2:]); w.close()
+    assert np.array_equal(chains.read_packed(base2)[0], full)
+
+
+def test_histogram_quantiles_match_numpy_percentiles():
+    """stats.quantiles_from_hist (the host end of lapf_sampler_sketch) against np.percentile of the
+    values the histogram was filled from: equal to within one bin width."""
+    import torch
+    from olpefit_b200 import stats
+    rng = np.random.default_rng(11)
+    n_bins, width, centre = 2048, 2e-3, 12.03
+    x = np.concatenate([rng.normal(12.031, 0.04, 150000), rng.normal(12.2, 0.01, 3000)])
+    pos = np.floor((x - centre) / width) + n_bins // 2
+    b = np.where(pos < 0, 0, np.where(pos >= n_bins, n_bins + 1, pos + 1)).astype(int)
+    hist = np.bincount(b, minlength=n_bins + 2)
+    q = stats.quantiles_from_hist(torch.tensor(hist)[None], torch.tensor([centre]), torch.tensor([[width]]))[0].numpy()
+    ref = np.percentile(x, [15.865, 50.0, 84.135])
+    assert np.max(np.abs(q - ref)) < width
+    # nothing recorded, or the quantile lies outside the range: nan, not a made-up number
+    empty = stats.quantiles_from_hist(torch.zeros((1, n_bins + 2)), torch.tensor([centre]), torch.tensor([[width]]))
+    assert bool(torch.isnan(empty).all())
+    far = np.zeros(n_bins + 2); far[-1] = 10
+    assert bool(torch.isnan(stats.quantiles_from_hist(torch.tensor(far)[None], torch.tensor([centre]), torch.tensor([[width]]))).all())
