@@ -50,12 +50,22 @@ def parse_args():
     ap.add_argument("--ref-updates-per-step", type=int, default=4000, help="updates per CPU walker and step, --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the 1-walker / 64-walker block (BASELINE configs 1-2)")
     return ap.parse_args()
 
 
 def workload_name(a):
     return ("config3: %d walkers/GPU x %d epochs, %dx%d stamps, %d-body, %d updates/step"
             % (a.walkers, a.frames, a.stamp, a.stamp, a.nbody, a.updates_per_step))
+
+
+def workload_config(a):
+    """The keys both arms print, so the two lines describe the same workload."""
+    return {"workload": workload_name(a), "walkers_per_gpu": a.walkers, "frames": a.frames, "stamp": a.stamp,
+            "nbody": a.nbody, "updates_per_step": a.updates_per_step, "thin": a.thin, "team_warps": a.team,
+            "l2": "GPU arm: L2 flushed between timed steps (256 MiB memset outside the event pairs), stamps re-staged "
+                  "from HBM into shared memory by TMA in every launch; CPU arm (--impl reference): a bounded sample of "
+                  "the same workload on the host cores, no device involved"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -128,7 +138,10 @@ def run_reference(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "gibbs_updates_per_sec": total_updates / secs,
-        "config": {"workload": workload_name(a)},
+        "config": workload_config(a),
+        "sample": "this arm runs a bounded SAMPLE of the workload: %d host walkers (one process per core) x %d "
+                  "updates per step on epoch 0 of the same %dx%d stamps; the rate per update does not depend on "
+                  "the number of walkers or epochs" % (cores, per_step, a.stamp, a.stamp),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d host walkers (one process each) x %d updates per step on epoch 0, "
                                    "%dx%d stamp, float64 numpy restatement of apf_step2.py:300-351 "
@@ -192,6 +205,43 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # GPU side
 # ----------------------------------------------------------------------------------------------
+def latency_block(a, dev):
+    """BASELINE.json configs[0] and [1] -- one walker (apf_step2a) and 64 walkers (apf_step2 under
+    mpiexec -n 64) on the 1024 x 1024 frame -- through the product path of the command lines:
+    128-pixel stamp, whole-frame chi-square (the pixels outside the stamp through their sums), 16
+    warps per walker.  Latency-bound by nature: reported beside the throughput line, not as it."""
+    import torch
+    from olpefit_b200 import frame, sampler, synth
+    out = {}
+    img, _ = synth.make_frame(0, a.nbody)
+    size = 128
+    ox, oy = synth.stamp_origin(size, a.nbody)
+    guess = synth.step1_guess(img, a.nbody)
+    p0 = frame.initial_parameters(img, guess, a.nbody)
+    dom = frame.prepare_domain(torch.from_numpy(img).to(dev), HEADER, size=size, cut=(ox, oy), nbody=a.nbody,
+                               device=str(dev), whole_frame=True)
+    for name, walkers, n_upd in (("config1_one_walker", 1, 8192), ("config2_64_walkers", 64, 4096)):
+        with sampler.GibbsSampler(dom, np.tile(p0, (walkers, 1)), seed=a.seed, burn_in=0, thin=16, team_warps=16) as s:
+            s.run(256, record=False)                                  # warm-up
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = None
+            for _ in range(3):
+                e0.record()
+                s.run(n_upd, record=False)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+        out[name] = {"walkers": walkers, "stamp": size, "domain": "frame (1024 x 1024 through the outside sums)",
+                     "team_warps": 16, "updates_per_launch": n_upd, "ms_per_launch": best,
+                     "us_per_update_per_walker": 1e3 * best / n_upd,
+                     "gibbs_updates_per_sec": walkers * n_upd / (best * 1e-3),
+                     "pixel_model_evals_per_sec": walkers * n_upd * 1024.0 * 1024.0 / (best * 1e-3)}
+    out["note"] = ("pixel_model_evals_per_sec counts the reference's domain (1024 x 1024 pixels per update); the Gaussians "
+                   "are evaluated on the 128-pixel stamp, the rest of the frame enters through its exact sums")
+    return out
+
+
 def run_b200(a):
     cpu = None
     world_env = int(os.environ.get("WORLD_SIZE", 1))
@@ -290,30 +340,49 @@ def run_b200(a):
     # epochs would.
     e2e = None
     if not a.no_e2e:
-        chain_h = torch.empty((max(rows, 1), W, P + 1), dtype=torch.float64).pin_memory()
+        # chain rows leave the device as float32 differences from each walker's starting point
+        # (LAPF_CHAIN_F32_DELTA: half the bytes, the values are restored exactly enough on the host)
+        smp.set_chain_format("f32delta")
+        chain32 = torch.empty((max(rows, 1), W, P + 1), dtype=torch.float32, device=dev)
+        chain_h = torch.empty((max(rows, 1), W, P + 1), dtype=torch.float32).pin_memory()
         tot_h = torch.empty((2 * P + 1,), dtype=torch.int64).pin_memory()
         frames_d = torch.empty_like(frames_h, device=dev)
         init_d = torch.empty_like(init_h, device=dev)
         h2d = frames_h.numel() * 4 + init_h.numel() * 8
-        d2h = chain_h.numel() * 8 + tot_h.numel() * 8
+        d2h = chain_h.numel() * 4 + tot_h.numel() * 8
         n_e2e = max(3, a.steps)
         times = []
+        names = ["h2d", "frame_prep", "reset_initial_chi2", "gibbs_updates", "d2h"]
+        marks = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(n_e2e + 1)]
+        host_ms = []
         for i in range(n_e2e + 1):
             torch.cuda.synchronize()
             dist.barrier()
             t0 = time.perf_counter()
+            mk = marks[i]
+            mk[0].record()
             frames_d.copy_(frames_h, non_blocking=True)
             init_d.copy_(init_h, non_blocking=True)
+            mk[1].record()
             frame.prepare_domain(frames_d, HEADER, origin=origins, nbody=a.nbody, into=dom)
+            mk[2].record()
             smp.reset(init_d, seed=a.seed + 1 + i)
-            ch = smp.run(U, out=chain)
+            mk[3].record()
+            ch = smp.run(U, out=chain32)
+            mk[4].record()
             chain_h.copy_(ch, non_blocking=True)
             stt = smp.stats(moments=False)
             tot_h.copy_(torch.cat([stt["tries"], stt["accepts"], stt["min_tries"].reshape(1)]), non_blocking=True)
+            mk[5].record()
+            t_issue = time.perf_counter() - t0              # the host has queued the whole step
             torch.cuda.synchronize()
             dist.barrier()
             if i > 0:
                 times.append(time.perf_counter() - t0)
+                host_ms.append(1e3 * t_issue)
+        phases = {nm: statistics.median(marks[i][j].elapsed_time(marks[i][j + 1]) for i in range(1, n_e2e + 1))
+                  for j, nm in enumerate(names)}
+        phases["host_issue"] = statistics.median(host_ms)
         if os.environ.get("LAPF_BENCH_DEBUG"):
             sys.stderr.write("e2e step times (ms): %s\n" % ["%.1f" % (1e3 * t) for t in times])
         # the same steps as a STREAM of epochs through the public double-buffered chain output
@@ -369,6 +438,11 @@ def run_b200(a):
                        "a copy stream (ChainStreamer) so they overlap the next batch; wall clock between the "
                        "arrivals of consecutive batches in host memory, median over steps (mean = total / steps "
                        "beside it), max over ranks" % U,
+               "chain_rows": "float32 differences from the starting points (LAPF_CHAIN_F32_DELTA)",
+               "phases_ms": dict({k: round(v, 3) for k, v in phases.items()},
+                                 note="device time of each phase of one batch processed alone (CUDA events, median "
+                                      "over steps, this rank) and the host time to queue the step; in the stream "
+                                      "the d2h of batch i overlaps the phases of batch i+1"),
                "one_batch_at_a_time": {
                    "value": float(W) * U * world * S * S / t_med, "ms_per_step": 1e3 * t_med,
                    "ms_per_step_mean": 1e3 * t_mean, "ms_per_step_min": 1e3 * min(times),
@@ -377,6 +451,7 @@ def run_b200(a):
                            "wall clock per step, median over steps, max over ranks"}}
 
     smp.close()
+    latency = latency_block(a, dev) if (rank == 0 and not a.no_latency) else None
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -413,30 +488,55 @@ def run_b200(a):
     pw = min(S, 64)
     tab_ex2 = (S // 2) * 16 + (S // pw) * (S // tr) * (pw // 4) * K * 8
     ex2_exec = comp_rate / 8.0 + upd_rate * tab_ex2
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            tj = json.load(fh)
-        key = "%d-body %dx%d W=%d F=%d U=%d" % (a.nbody, S, S, W, F, U)
-        traffic = tj.get(key)
-    except Exception:
-        traffic = None
+    key = "%d-body %dx%d W=%d F=%d U=%d" % (a.nbody, S, S, W, F, U)
+    traffic, ncu = None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):          # per-launch DRAM bytes from the ncu --set full capture
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                tj = json.load(fh)
+            if key in tj:
+                traffic, ncu = tj[key], tj.get(key + " ncu")
+                break
+        except Exception:
+            pass
+    cyc_per_update = secs * f_run * 1e6 * sm_count * 4 / (updates / world)      # per scheduler (4 per SM)
+    steps_per_update = (S // (4 if S >= 64 else 8)) * max(1, S // 64)
+    exec_flops = 2.0 * lane_ops
     roofline = {
         "bound": "fp32", "kernel": ("gibbs_batch_kernel<%d,%d>" if a.team == 1 else "gibbs_kernel<%d,%d>") % (a.nbody, S),
-        "achieved": alg_flops / 1e12, "peak": fp32_peak_flops / 1e12, "unit": "TFLOP/s",
-        "frac": alg_flops / fp32_peak_flops,
-        "algorithmic": "%d flops (= %d FP32 instructions) and %d ex2 per pixel-model evaluation, SURVEY.md 8(d)"
-                       % (7 * K + 4, 4 * K + 3, K),
+        # the top-level numbers are what the silicon EXECUTES: FP32 lane operations of the pixel loop (FFMA = 2 flops)
+        "achieved": exec_flops / 1e12, "peak": fp32_peak_flops / 1e12, "unit": "TFLOP/s",
+        "frac": exec_flops / fp32_peak_flops,
+        "what": "executed FP32 lane operations of the pixel loop ((10NB+8)/(8NB) per component evaluation left after "
+                "far-field culling, from the device counter, + 2 per pixel) x 2 flops, against the measured FFMA-stream "
+                "peak; tables, proposals and reductions are overhead and not counted",
         "peak_source": "measured on this device by lapf_measure_peaks (dependent-free FFMA stream x 2 flops); "
                        "MEASURED_PEAKS.json has no FP32 entry",
-        "peak_nominal_at_run_clock": fp32_nominal / 1e12, "frac_nominal_at_run_clock": alg_flops / fp32_nominal,
+        "peak_nominal_at_run_clock": fp32_nominal / 1e12, "frac_nominal_at_run_clock": exec_flops / fp32_nominal,
         "executed": {
             "fp32_lane_ops_per_s": lane_ops, "fp32_lane_op_peak": pk[1], "frac": lane_ops / pk[1],
             "component_evals_per_pixel_eval": comp_rate / per_gpu,
             "ex2_per_s": ex2_exec, "ex2_per_pixel_eval": ex2_exec / per_gpu,
-            "note": "FP32 lane operations of the pixel loop only (tables, proposals and reductions are overhead): "
-                    "(10NB+8)/(8NB) per component evaluation + 2 per pixel; component evaluations from the device "
-                    "counter (far-field culling skips the rest)",
+            "cycles_per_update_per_scheduler": cyc_per_update,
+            "warp_steps_per_update": steps_per_update,
+        },
+        # the bound of the factorised loop, from tools/microbench7.cu on this GPU (profiles/r02_microbench7.txt):
+        # a packed FFMA2 holds the FP32 pipe for 2 cycles, and for 3 when its three operand pairs all have to be
+        # fetched from the register file; nothing else issues in its shadow
+        "dispatch_model": {
+            "fma_pipe_cycles_per_warp_step": 32 * 2 + 8,
+            "operand_fetch_cycles_per_warp_step": 24 * 2.2 + 8 * 3.0 + 8 * 1.64,
+            "other_instructions_per_warp_step": 17,
+            "note": "2-body warp step (8 pixels x 4 components per lane): 32 packed + 8 scalar FP32 instructions + 4 "
+                    "MUFU + 6 LDS.128 + 1 LDTM; measured costs: FFMA2 2.2 cycles with a reused operand, 3.0 with three "
+                    "distinct pairs, FFMA 1.64 with distinct registers -> ~107 cycles per step per scheduler",
+        },
+        "ncu": ncu,                                                  # issue active, pipe utilisation of the committed capture
+        "algorithmic": {
+            "achieved": alg_flops / 1e12, "frac": alg_flops / fp32_peak_flops,
+            "note": "SURVEY.md 8(d)'s count, %d flops (= %d FP32 instructions) and %d ex2 per pixel-model evaluation, x the "
+                    "measured rate: credits work the factorised loop does not execute (not a utilisation)"
+                    % (7 * K + 4, 4 * K + 3, K),
         },
         "sfu": {
             "achieved": ex2_alg / 1e9, "peak": pk[0] / 1e9, "unit": "Gex2/s", "frac": ex2_alg / pk[0],
@@ -451,14 +551,11 @@ def run_b200(a):
         "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "gibbs_updates_per_sec": updates / secs,
-        "config": {"workload": workload_name(a), "walkers_per_gpu": W, "frames": F, "stamp": S,
-                   "nbody": a.nbody, "updates_per_step": U, "thin": a.thin, "team_warps": a.team,
-                   "l2": "flushed between timed steps (256 MiB memset outside the event pairs); stamps are "
-                         "re-staged from HBM into shared memory by TMA in every launch",
-                   "timing": "CUDA events around each step on the launch stream, summed; max over ranks",
+        "config": workload_config(a),
+        "timing": {"how": "CUDA events around each step on the launch stream, summed; max over ranks",
                    "wall_ms_per_step_incl_flush": 1e3 * t_wall / a.steps},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(gpu_launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
         "acceptance_rate_mean": float(np.mean(acc_rate)), "min_tries": int(min_tries.item()),
     }
     emit(line)

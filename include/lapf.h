@@ -51,7 +51,8 @@ typedef enum lapf_status {
     LAPF_ERR_INVALID = -1,      /* bad argument / unsupported shape */
     LAPF_ERR_CUDA = -2,         /* a CUDA runtime call failed (see lapf_last_error) */
     LAPF_ERR_NO_DEVICE = -3,    /* no sm_100 device: there is no CPU path */
-    LAPF_ERR_NOMEM = -4
+    LAPF_ERR_NOMEM = -4,
+    LAPF_ERR_SELFTEST = -5      /* the batched sampler of this build disagrees with the stateless operator */
 } lapf_status;
 
 /* The pixel domain: F frames (epochs), each an ny x nx cut-out ("stamp") or a full frame.
@@ -118,6 +119,16 @@ int lapf_model_chi2(const lapf_problem* prob, const double* params, int64_t B,
  * initial chi-square (apf_step2.py:283-289) and zeroes the try/accept counters (:276). */
 int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream);
 int lapf_sampler_destroy(lapf_sampler* s);
+
+/* Self-test of the batched sampler (team_warps 0/1), run by lapf_sampler_create unless the
+ * environment variable LAPF_NO_SELFTEST is set: three updates of every walker, each one recorded,
+ * whose TRIAL chi-squares (apf_step2.py:314-316) are compared bit for bit with lapf_model_chi2 of
+ * the same trial vectors; then the sampler is put back exactly as it was (checkpoint round trip).
+ * liblapf.so is rebuilt in-tree with whatever nvcc the box has; the sampler kernel keeps its pixels
+ * in tensor memory behind `.sync.aligned` loads, and one experimental build of it evaluated the
+ * update after every recorded update wrongly while passing every state-based check.
+ * Returns LAPF_ERR_SELFTEST on any difference.  Synchronises the stream. */
+int lapf_sampler_selftest(lapf_sampler* s, void* stream);
 
 /* Start a new batch in an existing sampler: new starting points (device [n_walkers][P]) and seed,
  * counters, moments and update count back to zero, initial chi-square re-evaluated against the

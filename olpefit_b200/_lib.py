@@ -38,6 +38,7 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p]),
     "lapf_sampler_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p), C.c_void_p]),
     "lapf_sampler_destroy": (C.c_int, [C.c_void_p]),
+    "lapf_sampler_selftest": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lapf_sampler_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "lapf_sampler_checkpoint_bytes": (C.c_int64, [C.c_void_p]),
     "lapf_sampler_save": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -269,6 +269,7 @@ struct RunArgs {
     double* sk_mom;              // [W][NB-1][2][2]: per walker sum / sum of squares of (value - centre)
     double sk_inv_sep, sk_inv_pa;   // 1 / bin width
     int sk_bins, chain_f32;
+    double* probe;               // self-test only: [rows][W][3] = parameter index, proposed value, TRIAL chi-square
     int64_t n_walkers;
     int64_t t0, n_updates;       // first update index, updates in this launch
     int64_t next_record;         // first count >= t0+1 at which a row is recorded
@@ -609,6 +610,10 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
                     for (int j = 0; j < 2 * NB; ++j) xy[j] = st[j];
                     record_sketch<NB>(a, wl, frame, xy);
                 }
+                if (a.probe) {                                            // lapf_sampler_selftest
+                    double* pb = a.probe + ((size_t)row * a.n_walkers + wl) * 3;
+                    pb[0] = (double)k; pb[1] = nv; pb[2] = chi_t;
+                }
             }
             ++row;
             next_rec += a.thin;   // (saturates harmlessly: a launch is shorter than 2^30)
@@ -689,6 +694,32 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
         tmem_fence_before_sync();
         __syncthreads();
         if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
+    }
+}
+
+// lapf_sampler_selftest: trial vector of update u = state before it (start, or the row recorded by
+// update u-1) with the proposed value in place; and the comparison of the sampler's trial
+// chi-squares with the stateless operator's, bit for bit.
+__global__ void selftest_trials_kernel(const double* __restrict__ start, const double* __restrict__ chain,
+                                       const double* __restrict__ probe, int U, int64_t W, int P,
+                                       double* __restrict__ trials /*[U][W][P]*/) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)U * W) return;
+    const int64_t u = i / W, w = i % W;
+    const double* before = u ? chain + ((u - 1) * W + w) * (P + 1) : start + w * (P + 1);
+    const int k = (int)probe[i * 3];
+    for (int j = 0; j < P; ++j) trials[i * P + j] = (j == k) ? probe[i * 3 + 1] : before[j];
+}
+
+__global__ void selftest_compare_kernel(const double* __restrict__ probe, const double* __restrict__ chi_k1, int64_t n,
+                                        unsigned long long* __restrict__ out /*[2]: mismatches, first index + 1*/) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = probe[i * 3 + 2], b = chi_k1[i];
+    const bool same = (a == b) || (isnan(a) && isnan(b));
+    if (!same) {
+        atomicAdd(out, 1ull);
+        atomicMin(out + 1, (unsigned long long)i + 1ull);
     }
 }
 
@@ -972,6 +1003,7 @@ struct lapf_sampler {
     int32_t* item_first = nullptr;
     int32_t* item_count = nullptr;
     int32_t* cta_item = nullptr;   // batched kernel: first item of every CTA
+    int32_t* frame_of = nullptr;   // [W] the caller's frame index per walker (a copy: reset and the self-test need it)
     // chain rows leave as double values or as float differences from the starting point
     int chain_format = LAPF_CHAIN_F64;
     // separation / position-angle sketches (lapf_sampler_sketch_enable)
@@ -1221,7 +1253,7 @@ static void free_sampler(lapf_sampler* s) {
     if (!s) return;
     cudaFree(s->state); cudaFree(s->shift); cudaFree(s->moments); cudaFree(s->tries); cudaFree(s->accepts); cudaFree(s->exps);
     cudaFree(s->walker_of); cudaFree(s->frame_start); cudaFree(s->item_frame); cudaFree(s->item_first);
-    cudaFree(s->item_count); cudaFree(s->cta_item);
+    cudaFree(s->item_count); cudaFree(s->cta_item); cudaFree(s->frame_of);
     cudaFree(s->sk_hist); cudaFree(s->sk_center); cudaFree(s->sk_mom);
     delete s;
 }
@@ -1332,6 +1364,9 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     CUS(cudaMalloc((void**)&s->item_first, sizeof(int32_t) * s->n_items));
     CUS(cudaMalloc((void**)&s->item_count, sizeof(int32_t) * s->n_items));
     CUS(cudaMalloc((void**)&s->cta_item, sizeof(int32_t) * cta_item.size()));
+    CUS(cudaMalloc((void**)&s->frame_of, sizeof(int32_t) * W));
+    CUS(cudaMemcpyAsync(s->frame_of, fo.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, st));
+    s->cfg.frame_of = s->frame_of;
     CUS(cudaMemcpyAsync(s->walker_of, order.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, st));
     CUS(cudaMemcpyAsync(s->frame_start, start.data(), sizeof(int32_t) * (F + 1), cudaMemcpyHostToDevice, st));
     CUS(cudaMemcpyAsync(s->item_frame, it_frame.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
@@ -1342,6 +1377,8 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     CUS(cudaStreamSynchronize(st));   // the host vectors above are pageable
     rc = lapf_sampler_reset(s, cfg->init_params, cfg->seed, st);
     if (rc) { free_sampler(s); return rc; }
+    // three probe updates against the stateless operator, then the state is put back (LAPF_NO_SELFTEST=1 skips it)
+    if (!getenv("LAPF_NO_SELFTEST") && (rc = lapf_sampler_selftest(s, st))) { free_sampler(s); return rc; }
 #undef CUS
     *out = s;
     return LAPF_OK;
@@ -1460,16 +1497,8 @@ int64_t lapf_sampler_rows_for(const lapf_sampler* s, int64_t n_updates) {
 int64_t lapf_sampler_count(const lapf_sampler* s) { return s ? s->count : fail(LAPF_ERR_INVALID, "sampler is NULL"); }
 int64_t lapf_sampler_launches(const lapf_sampler* s) { return s ? s->launches : fail(LAPF_ERR_INVALID, "sampler is NULL"); }
 
-int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, void* chain_out, int64_t rows_cap, void* stream) {
-    if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
-    if (n_updates < 0 || n_updates > ((int64_t)1 << 30))
-        return fail(LAPF_ERR_INVALID, "n_updates must be in [0, 2^30] per launch");
-    if (n_updates == 0) return LAPF_OK;
-    const int64_t rows = lapf_sampler_rows_for(s, n_updates);
-    if (chain_out && rows_cap < rows)
-        return fail(LAPF_ERR_INVALID, "chain_out holds %lld rows but this run records %lld", (long long)rows_cap, (long long)rows);
+static void fill_run_args(const lapf_sampler* s, RunArgs& a, int64_t n_updates, void* chain_out) {
     const lapf_problem& pb = s->cfg.problem;
-    RunArgs a;
     a.data = pb.data; a.weight = pb.weight; a.origin = pb.origin; a.outside = pb.outside;
     a.item_frame = s->item_frame; a.item_first = s->item_first; a.item_count = s->item_count;
     a.walker_of = s->walker_of; a.cta_item = s->cta_item;
@@ -1491,6 +1520,19 @@ int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, void* chain_out, int64_
     a.thin = s->cfg.thin; a.floor_index = pb.floor_index; a.n_items = s->n_items;
     a.cull = cull_enabled(&pb);
     a.plain = plain_loop(&pb);
+    a.probe = nullptr;
+}
+
+int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, void* chain_out, int64_t rows_cap, void* stream) {
+    if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
+    if (n_updates < 0 || n_updates > ((int64_t)1 << 30))
+        return fail(LAPF_ERR_INVALID, "n_updates must be in [0, 2^30] per launch");
+    if (n_updates == 0) return LAPF_OK;
+    const int64_t rows = lapf_sampler_rows_for(s, n_updates);
+    if (chain_out && rows_cap < rows)
+        return fail(LAPF_ERR_INVALID, "chain_out holds %lld rows but this run records %lld", (long long)rows_cap, (long long)rows);
+    RunArgs a;
+    fill_run_args(s, a, n_updates, chain_out);
     int rc = launch_dispatch(s, a, (cudaStream_t)stream);
     if (rc) return rc;
     s->count += n_updates;
@@ -1533,6 +1575,79 @@ int lapf_sampler_stats(lapf_sampler* s, int64_t* totals_out, double* moments_out
         CU(cudaGetLastError());
         s->launches++;
     }
+    return LAPF_OK;
+}
+
+int lapf_sampler_selftest(lapf_sampler* s, void* stream) {
+    if (!s) return fail(LAPF_ERR_INVALID, "sampler is NULL");
+    if (s->team != 1) return LAPF_OK;                       // the team kernels keep no TMEM pixel store
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = s->P, U = 3;
+    const int64_t W = s->cfg.n_walkers;
+    const size_t nst = (size_t)W * (P + 1), blob_bytes = checkpoint_bytes(s);
+    unsigned char* blob = nullptr;
+    double *chain = nullptr, *probe = nullptr, *trials = nullptr, *chi = nullptr, *start = nullptr;
+    int32_t* fo = nullptr;
+    unsigned long long* out = nullptr;
+    auto cleanup = [&]() {
+        for (void* q : {(void*)blob, (void*)chain, (void*)probe, (void*)trials, (void*)chi, (void*)start, (void*)fo, (void*)out})
+            if (q) cudaFreeAsync(q, st);
+    };
+#define CUT(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            cleanup();                                                                             \
+            return fail(LAPF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+    CUT(cudaMallocAsync((void**)&blob, blob_bytes, st));
+    CUT(cudaMallocAsync((void**)&chain, sizeof(double) * nst * U, st));
+    CUT(cudaMallocAsync((void**)&probe, sizeof(double) * (size_t)W * 3 * U, st));
+    CUT(cudaMallocAsync((void**)&trials, sizeof(double) * (size_t)W * P * U, st));
+    CUT(cudaMallocAsync((void**)&chi, sizeof(double) * (size_t)W * U, st));
+    CUT(cudaMallocAsync((void**)&start, sizeof(double) * nst, st));
+    CUT(cudaMallocAsync((void**)&fo, sizeof(int32_t) * (size_t)W * U, st));
+    CUT(cudaMallocAsync((void**)&out, 16, st));
+    int rc = lapf_sampler_save(s, blob, (int64_t)blob_bytes, st);
+    if (rc) { cleanup(); return rc; }
+    CUT(cudaMemcpyAsync(start, s->state, sizeof(double) * nst, cudaMemcpyDeviceToDevice, st));
+    for (int u = 0; u < U; ++u)
+        CUT(cudaMemcpyAsync(fo + (size_t)u * W, s->frame_of, sizeof(int32_t) * W, cudaMemcpyDeviceToDevice, st));
+    // U updates, every one recorded (the build that failed mis-evaluated the update AFTER a recorded one), rows as
+    // doubles, no sketches; the trial chi-squares leave through `probe`
+    RunArgs a;
+    fill_run_args(s, a, U, chain);
+    a.thin = 1;
+    a.next_record = a.t0 + 1;
+    a.chain_f32 = 0;
+    a.sk_hist = nullptr;
+    a.probe = probe;
+    rc = launch_dispatch(s, a, st);
+    if (rc) { cleanup(); return rc; }
+    const int64_t n = (int64_t)U * W;
+    selftest_trials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(start, chain, probe, U, W, P, trials);
+    CUT(cudaGetLastError());
+    rc = lapf_model_chi2(&s->cfg.problem, trials, n, fo, nullptr, chi, st);
+    if (rc) { cleanup(); return rc; }
+    const unsigned long long init[2] = {0ull, ~0ull};
+    CUT(cudaMemcpyAsync(out, init, 16, cudaMemcpyHostToDevice, st));
+    selftest_compare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(probe, chi, n, out);
+    CUT(cudaGetLastError());
+    unsigned long long res[2] = {0, 0};
+    CUT(cudaMemcpyAsync(res, out, 16, cudaMemcpyDeviceToHost, st));
+    rc = lapf_sampler_load(s, blob, (int64_t)blob_bytes, st);      // synchronises the stream: `init` and `res` are settled
+    if (rc) { cleanup(); return rc; }
+    CUT(cudaStreamSynchronize(st));
+    cleanup();
+#undef CUT
+    s->launches += 3;
+    if (res[0] != 0)
+        return fail(LAPF_ERR_SELFTEST,
+                    "self-test failed: %llu of %lld trial chi-squares of the batched sampler differ from the stateless "
+                    "operator (first: update %lld of walker %lld).  This build of liblapf.so mis-compiles the sampler "
+                    "kernel; rebuild with the CUDA toolkit the tests were run with (see DESIGN.md 10).",
+                    res[0], (long long)n, (long long)((res[1] - 1) / W), (long long)((res[1] - 1) % W));
     return LAPF_OK;
 }
 

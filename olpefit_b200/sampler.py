@@ -117,7 +117,7 @@ class GibbsSampler:
         return out
 
     # -- separation / position angle without the chain (apf_step3.py:255-256,283-291,436-437) ---------
-    def enable_sketch(self, n_bins=8192, sep_bin=5e-4, pa_bin=2e-3, centers=None):
+    def enable_sketch(self, n_bins=16384, sep_bin=5e-4, pa_bin=2e-3, centers=None):
         """From now on every recorded row enters per-frame histograms of separation (pixels) and
         position angle (degrees) of each companion; call before the first ``run``.  ``centers``:
         [F, nbody-1, 2] centre values (give every rank the same ones), default: the starting point

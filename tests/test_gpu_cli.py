@@ -120,10 +120,10 @@ def test_many_epochs_in_one_run_and_device_side_summary(tmp_path):
     for f in range(3):
         d = tmp_path / ("epoch%d" % f)
         d.mkdir()
-        img, _ = synth.make_frame(f, 2)
+        img, truth = synth.make_frame(f, 2)
         p = str(d / ("N2.2009053%d.2996%d.LDIF.fits" % (f, f)))
         frame.write_fits(p, img, synth.HEADER)
-        guess = synth.step1_guess(img, 2, sky_xy=(100, 120))
+        guess = [round(float(v), 1) for v in truth[:4]] + [100, 120]      # clicks refined by hand, as it were
         with open(chains.initial_guess_path(p), "w") as fh:
             fh.write(" ".join(str(v) for v in guess) + "\n")
         paths.append(p)

@@ -896,3 +896,93 @@ def test_outside_sums_kernel_matches_float64_numpy(gpu):
         inside[cuts[f, 1]:cuts[f, 1] + 128, cuts[f, 0]:cuts[f, 0] + 128] = True
         w = np.where(inside, 0.0, w)
         np.testing.assert_allclose(got[f], [w.sum(), (w * d).sum(), (w * d * d).sum()], rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: the pointwise parity test, wide (>= 1000 vectors per shape, masked cores,
+# negative pixels, both floors), with the worst errors written down as an artefact
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nbody", [2, 3])
+@pytest.mark.parametrize("size", [32, 64, 128])
+def test_k1_pointwise_parity_1000_vectors(gpu, nbody, size):
+    """1,000 seeded parameter vectors per shape in four frame variants -- the synthetic epoch as it
+    is, its star core above 0.8 x satlevel (masked pixels, apf_step2.py:188), a sky-subtracted copy
+    with negative pixels (err^2 = readnoise^2 + |image|, :207-210), and the --fix-bkgd floor -- against
+    the float64 oracle: per-pixel model within 1e-5 relative, chi-square within 1e-5 relative.  The
+    worst errors go to gpurun_out/r02_parity_errors.json (copied to profiles/)."""
+    import json
+    synth, model = gpu["synth"], gpu["model"]
+    lay = orc.layout_for(nbody)
+    ox, oy = synth.stamp_origin(size)
+    base, truth = synth.make_frame(5, nbody, region=(oy, oy + size, ox, ox + size))
+    tl = truth.copy()
+    tl[0:2 * nbody:2] -= ox
+    tl[1:2 * nbody:2] -= oy
+    rng = np.random.default_rng(1000 * size + nbody)
+    vecs = _random_vectors(tl, nbody, 1000, rng)
+    vecs[:, 0:2 * nbody:2] += ox
+    vecs[:, 1:2 * nbody:2] += oy
+    grid = orc.pixel_grid(size, size, (ox, oy))
+    variants = {"plain": (base, None), "masked_core": (base * np.float32(1.6), None),
+                "negative_pixels": (base - np.float32(120.0), None), "fix_bkgd": (base, 3 * nbody + 3)}
+    report = {}
+    for name, (img, floor_index) in variants.items():
+        dom = gpu["frame"].prepare_domain(img, HEADER, origin=(ox, oy), nbody=nbody, floor_index=floor_index)
+        img64 = img.astype(np.float64)
+        w = orc.weight_map(img64, HEADER)
+        if name == "masked_core":
+            assert (w == 0).sum() > 4 and np.array_equal(dom.weight[0].cpu().numpy() == 0, w == 0)
+        if name == "negative_pixels":
+            assert (img64 < 0).sum() > size
+        worst_px, worst_chi = 0.0, 0.0
+        for lo in range(0, 1000, 250):                     # model images of 250 vectors at a time
+            mod, chi = dom.model_chi2(vecs[lo:lo + 250], want_model=True)
+            mod, chi = mod.cpu().numpy(), chi.cpu().numpy()
+            for i in range(250):
+                m = orc.model_image(vecs[lo + i], lay, size, size, grid=grid, floor_index=floor_index)
+                worst_px = max(worst_px, float(np.max(np.abs(mod[i] - m) / np.abs(m))))
+                c = orc.chi_squared_weighted(img64, m, w)
+                worst_chi = max(worst_chi, abs(chi[i] - c) / abs(c))
+        report[name] = {"worst_pixel_rel": worst_px, "worst_chi2_rel": worst_chi}
+        assert worst_px < RTOL and worst_chi < RTOL, (name, worst_px, worst_chi)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r02_parity_errors.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    try:
+        with open(path) as fh:
+            allrep = json.load(fh)
+    except Exception:
+        allrep = {"tolerance": RTOL, "vectors_per_shape_and_variant": 1000, "oracle": "float64 numpy, oracle/lapf_oracle.py"}
+    allrep["%d-body %dx%d" % (nbody, size, size)] = report
+    with open(path, "w") as fh:
+        json.dump(allrep, fh, indent=1, sort_keys=True)
+    print("worst errors", nbody, size, report)
+
+
+def test_selftest_compares_trial_chi2_with_k1_and_restores_the_sampler(gpu, monkeypatch):
+    """lapf_sampler_selftest (run by lapf_sampler_create): three recorded probe updates whose TRIAL
+    chi-squares must equal the stateless operator bit for bit -- rejected proposals included, which
+    no state-based check sees -- and a sampler that continues exactly as if nothing had happened."""
+    torch = gpu["torch"]
+    from olpefit_b200 import _lib
+    lib = _lib.load()
+    for nbody, size, walkers in ((2, 32, 700), (3, 64, 600), (2, 128, 250)):
+        dom, stamps, origins, p0 = _sampler_setup(gpu, nbody, size, n_frames=2)
+        frame_of = (np.arange(walkers) % 2).astype(np.int32)
+        init = np.tile(p0, (walkers, 1))
+        kw = dict(seed=3, burn_in=4, thin=3)
+        with gpu["sampler"].GibbsSampler(dom, init, frame_of, **kw) as a:          # self-test inside create()
+            first = a.run(30)
+            sa = a.state()
+            _lib.check(lib.lapf_sampler_selftest(a._h, None))                          # and in the middle of a run
+            assert a.count == 30
+            for x, y in zip(sa, a.state()):
+                assert torch.equal(x, y)
+            rest = a.run(30)
+            stats_a = a.stats()
+        monkeypatch.setenv("LAPF_NO_SELFTEST", "1")
+        with gpu["sampler"].GibbsSampler(dom, init, frame_of, **kw) as b:
+            whole = b.run(60)
+            stats_b = b.stats()
+        monkeypatch.delenv("LAPF_NO_SELFTEST")
+        assert torch.equal(torch.cat([first, rest], dim=0), whole)
+        assert torch.equal(stats_a["moments"], stats_b["moments"]) and int(stats_a["exps"]) == int(stats_b["exps"])

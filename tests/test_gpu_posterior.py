@@ -19,39 +19,60 @@ HEADER = {"itime": 1.0, "coadds": 1, "multisam": 1, "sampmode": 2}
 QS = [15.865, 50.0, 84.135]
 
 
-@pytest.mark.parametrize("fixture", ["posterior_2body_s32.npz", "posterior_3body_s32.npz"])
-def test_separation_and_position_angle_posterior_match_cpu_reference(golden_dir, fixture):
+def _device_chain(z, plain_loop=False, walkers=2048, seed=20260101):
+    """The fixture's configuration on the device: same frame, same stamp, same starting point, same
+    burn-in / thinning; 2048 walkers on the Philox stream.  Returns (rows [rows, walkers, P+1], acceptance)."""
     import torch
-    from olpefit_b200 import chains, frame, sampler, synth
-
-    z = np.load(os.path.join(golden_dir, fixture))
+    from olpefit_b200 import frame, model, sampler, synth
     size, nbody, epoch = int(z["size"]), int(z["nbody"]), int(z["epoch"])
     ox, oy = (int(v) for v in z["origin"])
-    img, _ = synth.make_frame(epoch, nbody, region=(oy, oy + size, ox, ox + size))
-    dom = frame.prepare_domain(img, HEADER, origin=(ox, oy), nbody=nbody)
-    walkers = 2048
-    with sampler.GibbsSampler(dom, np.tile(z["p0"], (walkers, 1)), seed=20260101,
+    domain = str(z["domain"]) if "domain" in z.files else "stamp"
+    if domain == "frame":
+        # the reference's pixel domain: the whole 1024 x 1024 frame (apf_step2.py:94,134-137)
+        img, _ = synth.make_frame(epoch, nbody)
+        dom = frame.prepare_domain(img, HEADER, size=size, cut=(ox, oy), nbody=nbody, whole_frame=True)
+    else:
+        img, _ = synth.make_frame(epoch, nbody, region=(oy, oy + size, ox, ox + size))
+        dom = frame.prepare_domain(img, HEADER, origin=(ox, oy), nbody=nbody)
+    if plain_loop:
+        dom = model.PixelDomain(dom.data, dom.weight, dom.origin, nbody=nbody, outside=dom.outside, plain_loop=True)
+    with sampler.GibbsSampler(dom, np.tile(z["p0"], (walkers, 1)), seed=seed,
                               burn_in=int(z["burn"]), thin=int(z["thin"])) as s:
         chain = s.run(int(z["updates"]))
         st = s.stats()
         acc = (st["accepts"].double() / st["tries"].double()).cpu().numpy()
-    rows = chain.cpu().numpy()                                    # [rows, walkers, P+1]
-    n_cpu = int(z["walkers"])
+    rows = chain.cpu().numpy()
     assert rows.shape[0] == (int(z["updates"]) - int(z["burn"])) // int(z["thin"]) + 1
+    return rows, acc
+
+
+def _compare_quantiles(name, vals, q_cpu, q_walker_cpu, n_cpu):
+    """z-test of the pooled 16/50/84 % quantiles: standard errors from the spread between walkers."""
+    n_gpu = vals.shape[1]
+    q_gpu = np.percentile(vals, QS)
+    se_cpu = q_walker_cpu.std(axis=0, ddof=1) / np.sqrt(n_cpu)
+    se_gpu = np.percentile(vals, QS, axis=0).std(axis=1, ddof=1) / np.sqrt(n_gpu)
+    zscore = (q_gpu - q_cpu) / np.sqrt(se_cpu ** 2 + se_gpu ** 2)
+    print(name, "gpu", q_gpu, "cpu", q_cpu, "z", zscore)
+    assert np.all(np.abs(zscore) < 5.0), (name, q_gpu, q_cpu, zscore)
+    # and the 68% interval has the same width to a few per cent
+    assert (q_gpu[2] - q_gpu[0]) == pytest.approx(q_cpu[2] - q_cpu[0], rel=0.05)
+
+
+# the benchmark shapes (64: factorised loop + far-field culling + both planes in TMEM; 128 on the
+# reference's whole-frame domain: weight plane in TMEM) next to the 32-pixel ones, and the plain loop
+@pytest.mark.parametrize("fixture,plain_loop", [("posterior_2body_s32.npz", False), ("posterior_3body_s32.npz", False),
+                                                ("posterior_2body_s64.npz", False), ("posterior_2body_s64.npz", True),
+                                                ("posterior_2body_s128_frame.npz", False)])
+def test_separation_and_position_angle_posterior_match_cpu_reference(golden_dir, fixture, plain_loop):
+    from olpefit_b200 import chains
+    z = np.load(os.path.join(golden_dir, fixture))
+    rows, acc = _device_chain(z, plain_loop)
+    n_cpu, walkers = int(z["walkers"]), rows.shape[1]
 
     sep, pa = chains.separation_pa(rows[..., 0], rows[..., 1], rows[..., 2], rows[..., 3])
-    for name, vals, q_cpu, q_walker in (("sep", sep, z["sep_q"], z["sep_q_walker"]),
-                                        ("pa", pa, z["pa_q"], z["pa_q_walker"])):
-        q_gpu = np.percentile(vals, QS)
-        # Monte-Carlo standard error of each pooled CPU quantile from the spread between walkers;
-        # the same for the GPU walkers (32x more of them)
-        se_cpu = q_walker.std(axis=0, ddof=1) / np.sqrt(n_cpu)
-        se_gpu = np.percentile(vals, QS, axis=0).std(axis=1, ddof=1) / np.sqrt(walkers)
-        zscore = (q_gpu - q_cpu) / np.sqrt(se_cpu ** 2 + se_gpu ** 2)
-        print(name, "gpu", q_gpu, "cpu", q_cpu, "z", zscore)
-        assert np.all(np.abs(zscore) < 5.0), (name, q_gpu, q_cpu, zscore)
-        # and the 68% interval has the same width to a few per cent
-        assert (q_gpu[2] - q_gpu[0]) == pytest.approx(q_cpu[2] - q_cpu[0], rel=0.05)
+    _compare_quantiles("sep", sep, z["sep_q"], z["sep_q_walker"], n_cpu)
+    _compare_quantiles("pa", pa, z["pa_q"], z["pa_q_walker"], n_cpu)
 
     # every sampled parameter (not only the astrometry): pooled mean within Monte-Carlo error
     flat = rows.reshape(-1, rows.shape[-1])
@@ -67,6 +88,27 @@ def test_separation_and_position_angle_posterior_match_cpu_reference(golden_dir,
     t_sep, t_pa = orc.separation_pa(*z["truth"][:4])
     assert np.percentile(sep, 0.5) < t_sep < np.percentile(sep, 99.5)
     assert np.percentile(pa, 0.5) < t_pa < np.percentile(pa, 99.5)
+
+
+def test_posterior_from_the_step1_guess_matches_cpu_reference(golden_dir):
+    """Started from the raw step-1 guess (apf_step2.py:258-273) instead of the truth, at the
+    benchmark's 64-pixel stamp.  From there the reference's sampler itself is bimodal: a few per cent
+    of its walkers collapse the companion onto the star.  Both sides must show the same behaviour:
+    the same share of walkers on the star-companion solution, and there the same posterior."""
+    from olpefit_b200 import chains
+    z = np.load(os.path.join(golden_dir, "posterior_2body_s64_guess.npz"))
+    rows, acc = _device_chain(z)
+    n_cpu, walkers = int(z["walkers"]), rows.shape[1]
+    sep, pa = chains.separation_pa(rows[..., 0], rows[..., 1], rows[..., 2], rows[..., 3])
+    t_sep, t_pa = orc.separation_pa(*z["truth"][:4])
+    main = (np.abs(np.median(sep, axis=0) - t_sep) < 3.0) & (np.abs(np.median(pa, axis=0) - t_pa) < 2.0)
+    f_gpu, f_cpu = main.mean(), z["main_mode"].mean()
+    se = np.sqrt(max(f_cpu * (1 - f_cpu), 1.0 / n_cpu) / n_cpu + f_gpu * (1 - f_gpu) / walkers)
+    print("share of walkers on the main mode: gpu %.3f cpu %.3f (se %.3f)" % (f_gpu, f_cpu, se))
+    assert abs(f_gpu - f_cpu) < 4.0 * se
+    cm = z["main_mode"]
+    _compare_quantiles("sep", sep[:, main], z["sep_q_main"], z["sep_q_walker"][cm], int(cm.sum()))
+    _compare_quantiles("pa", pa[:, main], z["pa_q_main"], z["pa_q_walker"][cm], int(cm.sum()))
 
 
 def test_device_side_statistics_match_numpy(golden_dir):

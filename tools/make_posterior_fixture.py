@@ -7,6 +7,11 @@ what step 3 derives from such chains -- separation and position angle (apf_step3
 283-291) -- as pooled quantiles plus per-walker summaries (for Monte-Carlo standard errors).
 
     python tools/make_posterior_fixture.py [--walkers 64] [--updates 60000] [--burn 20000]
+                                           [--size 32|64|128] [--start truth|guess] [--domain stamp|frame]
+
+--domain frame adds the pixels of the 1024 x 1024 frame outside the stamp through their float64
+sums against the constant floor (what lapf_problem.outside does on the device; equal to the
+reference's whole-frame chi-square to 1e-7, tests/test_gpu_parity.py::test_whole_frame_domain_*).
 """
 import argparse
 import concurrent.futures as cf
@@ -20,8 +25,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 HEADER = {"itime": 1.0, "coadds": 1, "multisam": 1, "sampmode": 2}
-SIZE, EPOCH = 32, 0
+EPOCH = 0
 NBODY = int(os.environ.get("LAPF_FIXTURE_NBODY", "2"))
+SIZE = int(os.environ.get("LAPF_FIXTURE_SIZE", "32"))
+START = os.environ.get("LAPF_FIXTURE_START", "truth")
+DOMAIN = os.environ.get("LAPF_FIXTURE_DOMAIN", "stamp")
 
 
 def setup():
@@ -38,14 +46,34 @@ def setup():
     # walk the companion component onto the (initially badly fitted) star; that is a property of
     # the sampler, not something a CPU/GPU comparison should depend on.
     p0 = truth.copy()
-    return orc, lay, img, w, (ox, oy), p0, truth
+    if START == "guess":
+        p0 = orc.initial_parameters(img, g_local, lay)
+        p0[0:2 * NBODY:2] += ox
+        p0[1:2 * NBODY:2] += oy
+    outside = None
+    if DOMAIN == "frame":
+        full32, _ = synth.make_frame(EPOCH, NBODY)
+        full = full32.astype(np.float64)
+        wf = orc.weight_map(full, HEADER)
+        wf[oy:oy + SIZE, ox:ox + SIZE] = 0.0
+        outside = np.array([wf.sum(), (wf * full).sum(), (wf * full * full).sum()])
+    return orc, lay, img, w, (ox, oy), p0, truth, outside
 
 
 def walker(job):
     seed, n_updates, burn, thin = job
-    orc, lay, img, w, origin, p0, _ = setup()
+    orc, lay, img, w, origin, p0, _, outside = setup()
+    chi2_fn = None
+    if outside is not None:
+        ny, nx = img.shape
+        grid = orc.pixel_grid(ny, nx, origin)
+
+        def chi2_fn(q):
+            f = q[12]                                   # the reference's floor slot (apf_step2.py:119-120)
+            inside = orc.chi_squared_weighted(img, orc.model_image(q, lay, ny, nx, grid=grid), w)
+            return inside + outside[2] - 2.0 * f * outside[1] + f * f * outside[0]
     res = orc.run_chain(img, w, lay, p0, orc.NumpyStream(seed), origin=origin, n_updates=n_updates,
-                        burn_in=burn, thin=thin)
+                        burn_in=burn, thin=thin, chi2_fn=chi2_fn)
     return res.rows[1:], res.tries, res.accepts
 
 
@@ -55,8 +83,18 @@ def main():
     ap.add_argument("--updates", type=int, default=50000)
     ap.add_argument("--burn", type=int, default=10000)
     ap.add_argument("--thin", type=int, default=10)
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--start", default=None, choices=["truth", "guess"])
+    ap.add_argument("--domain", default=None, choices=["stamp", "frame"])
     a = ap.parse_args()
-    orc, lay, img, w, origin, p0, truth = setup()
+    global SIZE, START, DOMAIN
+    for name, val in (("LAPF_FIXTURE_SIZE", a.size), ("LAPF_FIXTURE_START", a.start), ("LAPF_FIXTURE_DOMAIN", a.domain)):
+        if val is not None:
+            os.environ[name] = str(val)                  # the spawned walkers read the configuration from the environment
+    SIZE = int(os.environ.get("LAPF_FIXTURE_SIZE", SIZE))
+    START = os.environ.get("LAPF_FIXTURE_START", START)
+    DOMAIN = os.environ.get("LAPF_FIXTURE_DOMAIN", DOMAIN)
+    orc, lay, img, w, origin, p0, truth, outside = setup()
     t0 = time.time()
     jobs = [(5000 + i, a.updates, a.burn, a.thin) for i in range(a.walkers)]
     with cf.ProcessPoolExecutor(max_workers=os.cpu_count(), mp_context=mp.get_context("spawn")) as ex:
@@ -66,10 +104,15 @@ def main():
     accepts = np.array([o[2] for o in out])
     sep, pa = orc.separation_pa(rows[..., 0], rows[..., 1], rows[..., 2], rows[..., 3])   # star -> first companion
     qs = [15.865, 50.0, 84.135]
+    # walkers whose chain sits on the star-companion solution (from the raw step-1 guess a few per cent of
+    # the reference's walkers collapse the companion onto the star instead: a property of the sampler)
+    t_sep0, t_pa0 = orc.separation_pa(truth[0], truth[1], truth[2], truth[3])
+    main = (np.abs(np.median(sep, axis=1) - t_sep0) < 3.0) & (np.abs(np.median(pa, axis=1) - t_pa0) < 2.0)
     res = {
-        "size": SIZE, "nbody": NBODY, "epoch": EPOCH, "p0": p0, "truth": truth, "origin": np.array(origin),
+        "size": SIZE, "nbody": NBODY, "epoch": EPOCH, "start": START, "domain": DOMAIN, "p0": p0, "truth": truth, "origin": np.array(origin),
         "updates": a.updates, "burn": a.burn, "thin": a.thin, "walkers": a.walkers,
         "sep_q": np.percentile(sep, qs), "pa_q": np.percentile(pa, qs),
+        "main_mode": main, "sep_q_main": np.percentile(sep[main], qs), "pa_q_main": np.percentile(pa[main], qs),
         "sep_q_walker": np.percentile(sep, qs, axis=1).T, "pa_q_walker": np.percentile(pa, qs, axis=1).T,
         "sep_mean_walker": sep.mean(axis=1), "pa_mean_walker": pa.mean(axis=1),
         "param_mean": rows.reshape(-1, rows.shape[-1]).mean(axis=0),
@@ -78,11 +121,13 @@ def main():
         "acceptance": accepts.sum(axis=0) / tries.sum(axis=0),
         "chi2_first_rows": rows[:, :5, -1], "chi2_last_rows": rows[:, -5:, -1],
     }
-    path = os.path.join(ROOT, "tests", "golden", "posterior_%dbody_s32.npz" % NBODY)
+    tag = ("" if START == "truth" else "_guess") + ("" if DOMAIN == "stamp" else "_frame")
+    path = os.path.join(ROOT, "tests", "golden", "posterior_%dbody_s%d%s.npz" % (NBODY, SIZE, tag))
     np.savez_compressed(path, **res)
     print("wrote", path, os.path.getsize(path), "bytes in %.0f s" % (time.time() - t0))
     print("sep quantiles", res["sep_q"], " SE(median) ~", res["sep_q_walker"][:, 1].std() / np.sqrt(a.walkers))
     print("pa quantiles", res["pa_q"], " SE(median) ~", res["pa_q_walker"][:, 1].std() / np.sqrt(a.walkers))
+    print("walkers on the main mode: %d of %d" % (main.sum(), a.walkers))
     print("acceptance", np.round(res["acceptance"], 3))
     print("chi2 at first recorded rows", res["chi2_first_rows"][:3], "last", res["chi2_last_rows"][:3])
     t_sep, t_pa = orc.separation_pa(truth[0], truth[1], truth[2], truth[3])
