@@ -266,6 +266,14 @@ def run_b200(a):
     rank, local_rank, world = dist.init()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
+    if world > 1:
+        # one slice of the host cores per rank: the ranks' Python threads and copy completions stop migrating
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per] or cores)
+        except (AttributeError, OSError):
+            pass
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()

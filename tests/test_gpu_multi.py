@@ -37,8 +37,8 @@ def _write_epochs(tmp_path, tag, n=3):
         img, truth = synth.make_frame(f, 2)
         p = str(d / ("N2.2009053%d.2996%d.LDIF.fits" % (f, f)))
         frame.write_fits(p, img, synth.HEADER)
-        with open(chains.initial_guess_path(p), "w") as fh:
-            fh.write(" ".join(str(round(float(v), 1)) for v in truth[:4]) + " 100 120\n")
+        os.makedirs(chains.results_dir(p))
+        chains.write_walker_csv(chains.results_dir(p) + "step2a.csv", np.concatenate([truth, [0.0]])[None])
         paths.append(p)
     lst = tmp_path / (tag + "_frames.txt")
     lst.write_text("\n".join(paths[1:]) + "\n")
@@ -51,9 +51,9 @@ def test_command_line_on_two_gpus_equals_one_gpu(tmp_path):
     common = ["--walkers", "7", "--accept-min", "30", "--burn-in", "50", "--seed", "77", "--stamp", "64", "--thin", "2",
               "--segment", "96", "--quiet"]
     p1, l1 = _write_epochs(tmp_path, "one")
-    assert cli.main_step2([p1[0], "--frames", l1] + common) == 0
+    assert cli.main_step2([p1[0], "-i", "2a", "--frames", l1] + common) == 0
     p2, l2 = _write_epochs(tmp_path, "two")
-    _torchrun([os.path.join(ROOT, "apf_step2.py"), p2[0], "--frames", l2] + common, 29621)
+    _torchrun([os.path.join(ROOT, "apf_step2.py"), p2[0], "-i", "2a", "--frames", l2] + common, 29621)
     for a, b in zip(p1, p2):
         da, db = chains.results_dir(a), chains.results_dir(b)
         for w in range(7):

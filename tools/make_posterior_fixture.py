@@ -52,8 +52,11 @@ def setup():
         p0[1:2 * NBODY:2] += oy
     outside = None
     if DOMAIN == "frame":
+        # the stamp is the cut-out of the full frame (a frame generated for a region alone is another noise realisation)
         full32, _ = synth.make_frame(EPOCH, NBODY)
         full = full32.astype(np.float64)
+        img = full[oy:oy + SIZE, ox:ox + SIZE].copy()
+        w = orc.weight_map(img, HEADER)
         wf = orc.weight_map(full, HEADER)
         wf[oy:oy + SIZE, ox:ox + SIZE] = 0.0
         outside = np.array([wf.sum(), (wf * full).sum(), (wf * full * full).sum()])
