@@ -826,11 +826,14 @@ def test_device_sketches_match_the_recorded_chain(gpu, nbody, team):
                 width = (sep_bin, pa_bin)[q]
                 c = summ[f, o - 1, q, 0]
                 assert summ[f, o - 1, q, 3] == rows * sel.sum() == hist[f, o - 1, q].sum()
-                pos = np.floor((vals - c) / width) + n_bins // 2
+                raw = (vals - c) / width
+                pos = np.floor(raw) + n_bins // 2
                 b = np.where(pos < 0, 0, np.where(pos >= n_bins, n_bins + 1, pos + 1)).astype(int)
                 ref_hist = np.bincount(b.ravel(), minlength=n_bins + 2)
-                # a value within rounding of a bin edge may fall on either side
-                assert np.abs(hist[f, o - 1, q] - ref_hist).sum() <= 4
+                # a value within rounding of a bin edge may fall on either side (walkers that have not moved
+                # yet sit exactly on the edge at the centre: device and numpy sqrt / atan2 differ in the last bit)
+                on_edge = int((np.abs(raw - np.rint(raw)) < 1e-6).sum())
+                assert np.abs(hist[f, o - 1, q] - ref_hist).sum() <= 2 * on_edge
                 assert summ[f, o - 1, q, 1] == pytest.approx((vals - c).sum(), rel=1e-9, abs=1e-9)
                 assert summ[f, o - 1, q, 2] == pytest.approx(((vals - c) ** 2).sum(), rel=1e-9)
                 # a histogram quantile is exact to its bin: the share of the values below (quantile - bin)

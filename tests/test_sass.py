@@ -45,10 +45,10 @@ def test_every_tmem_load_is_waited_for_before_its_registers_are_touched(kernels)
         assert gaps and min(gaps) >= 1, name
 
 
-def test_every_tmem_load_follows_a_convergence_point(kernels):
+def test_every_tmem_load_follows_an_unconditional_convergence_point(kernels):
+    """WARPSYNC.ALL (not just the BRA.DIV run-time check) between the warp's last possible divergence
+    and every `.sync.aligned` TMEM load: the one structural difference between the builds whose
+    sampler mis-evaluated the update after a recorded update and every build that works."""
     sass_check, fns, batch = kernels
     for name, ins in batch.items():
-        assert not sass_check.check_ldtm_convergence(ins), name
-        # every trip of a pixel loop re-converges the warp: as many WARPSYNC.ALL as loops with a TMEM load, at least
-        n_sync = sum(x.op == "WARPSYNC.ALL" for x in ins)
-        assert n_sync >= 6, (name, n_sync)
+        assert not sass_check.check_ldtm_convergence(ins), (name, sass_check.check_ldtm_convergence(ins))
