@@ -401,11 +401,26 @@ def run_b200(a):
         tot_hs = [torch.empty((2 * P + 1,), dtype=torch.int64).pin_memory() for _ in range(2)]
         got_rows = 0
 
+        # the upload of a batch runs on its own stream into one of two buffer pairs, so it overlaps the
+        # updates of the batch before (the host queues batch i+1 while batch i computes)
+        up_stream = torch.cuda.Stream(device=dev)
+        fr_d = [frames_d, torch.empty_like(frames_d)]
+        in_d = [init_d, torch.empty_like(init_d)]
+        uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
         def stream_step(i):
-            frames_d.copy_(frames_h, non_blocking=True)
-            init_d.copy_(init_h, non_blocking=True)
-            frame.prepare_domain(frames_d, HEADER, origin=origins, nbody=a.nbody, into=dom)
-            smp.reset(init_d, seed=a.seed + 100 + i)
+            j = i & 1
+            compute = torch.cuda.current_stream(dev)
+            up_stream.wait_event(consumed[j])              # the batch two steps ago has been read out of this pair
+            with torch.cuda.stream(up_stream):
+                fr_d[j].copy_(frames_h, non_blocking=True)
+                in_d[j].copy_(init_h, non_blocking=True)
+                uploaded[j].record(up_stream)
+            compute.wait_event(uploaded[j])
+            frame.prepare_domain(fr_d[j], HEADER, origin=origins, nbody=a.nbody, into=dom)
+            smp.reset(in_d[j], seed=a.seed + 100 + i)
+            consumed[j].record(compute)
             prev = streamer.run(U)
             stt = smp.stats(moments=False)
             tot_hs[i & 1].copy_(torch.cat([stt["tries"], stt["accepts"], stt["min_tries"].reshape(1)]), non_blocking=True)
@@ -441,7 +456,7 @@ def run_b200(a):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * t_stream, "ms_per_step_mean": 1e3 * t_total, "steps": n_e2e,
                "what": "a stream of batches through the public API: per step pinned host frames + starting "
-                       "points -> H2D -> frame prep (mask, noise map) -> sampler reset (initial chi-square) -> "
+                       "points -> H2D (own stream, double-buffered) -> frame prep (mask, noise map) -> sampler reset (initial chi-square) -> "
                        "%d updates -> chain rows + counters D2H to pinned host, the chain rows double-buffered on "
                        "a copy stream (ChainStreamer) so they overlap the next batch; wall clock between the "
                        "arrivals of consecutive batches in host memory, median over steps (mean = total / steps "

@@ -142,7 +142,8 @@ int lapf_sampler_reset(lapf_sampler* s, const double* init_params, uint64_t seed
  * its random stream is a pure function of (seed, walker id, update count), so a saved blob restores
  * the batch exactly: run(a); save; ...; load; run(b) gives the bits of run(a+b).  The blob is a
  * device buffer of lapf_sampler_checkpoint_bytes() bytes owned by the caller; load() expects a
- * sampler created with the same shape (walkers, model, frame_of).  The reference's only resume
+ * sampler created with the same shape (walkers, model, frame_of) and, if the sketches below are in
+ * use, with them enabled the same way before either call (they travel in the blob).  The reference's only resume
  * point is the chain file / step2a.csv (apf_step2.py:248-256). */
 int64_t lapf_sampler_checkpoint_bytes(const lapf_sampler* s);
 int lapf_sampler_save(lapf_sampler* s, void* blob, int64_t blob_bytes, void* stream);

@@ -46,7 +46,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
             os.unlink(tmp)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     os.replace(tmp, LIB)
+    # which toolchain produced this binary: the sampler kernel is sensitive to it, the
+    # self-test at sampler creation decides whether the build is usable, this file says what was used
+    try:
+        ver = subprocess.run([cmd[0], "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-2:]
+        with open(LIB + ".buildinfo", "w") as fh:
+            fh.write("nvcc: %s\nflags: %s\n" % (" | ".join(ver), " ".join(cmd[1:-len(SOURCES) - 2])))
+    except Exception:
+        pass
     return LIB
+
+
+def build_info() -> str:
+    """nvcc version and flags of the library on disk ('' if it was not built by this module)."""
+    try:
+        with open(LIB + ".buildinfo") as fh:
+            return fh.read()
+    except OSError:
+        return ""
 
 
 if __name__ == "__main__":

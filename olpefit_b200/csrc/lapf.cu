@@ -1420,11 +1420,18 @@ int lapf_sampler_reset(lapf_sampler* s, const double* init_params, uint64_t seed
 }
 
 // Checkpoint layout (device blob, 8-byte units): [count][seed][jump widths x LAPF_MAX_PARAMS] state shift
-// moments(2x) exps tries accepts
+// moments(2x) exps tries accepts [sketch sums, sketch histograms]
 constexpr size_t kCkptHead = 8 * (2 + LAPF_MAX_PARAMS);
+static size_t sketch_hist_bytes(const lapf_sampler* s) {
+    return s->sk_hist ? sizeof(uint32_t) * (size_t)s->cfg.problem.n_frames * 2 * (s->cfg.problem.nbody - 1) * (s->sk_bins + 2) : 0;
+}
+static size_t sketch_mom_bytes(const lapf_sampler* s) {
+    return s->sk_hist ? sizeof(double) * (size_t)s->cfg.n_walkers * 2 * (s->cfg.problem.nbody - 1) * 2 : 0;
+}
 static size_t checkpoint_bytes(const lapf_sampler* s) {
     const size_t W = (size_t)s->cfg.n_walkers, P = (size_t)s->P, nst = W * (P + 1);
-    return kCkptHead + sizeof(double) * nst * 4 + sizeof(unsigned long long) * W + sizeof(uint32_t) * W * P * 2;
+    return kCkptHead + sizeof(double) * nst * 4 + sizeof(unsigned long long) * W + sizeof(uint32_t) * W * P * 2 +
+           sketch_mom_bytes(s) + sketch_hist_bytes(s);      // the sketches too, once they are enabled
 }
 
 int64_t lapf_sampler_checkpoint_bytes(const lapf_sampler* s) {
@@ -1436,9 +1443,11 @@ static int checkpoint_copy(lapf_sampler* s, unsigned char* blob, bool save, cuda
     const size_t W = (size_t)s->cfg.n_walkers, P = (size_t)s->P, nst = W * (P + 1);
     struct Part { void* dev; size_t bytes; } parts[] = {
         {s->state, sizeof(double) * nst}, {s->shift, sizeof(double) * nst}, {s->moments, sizeof(double) * nst * 2},
-        {s->exps, sizeof(unsigned long long) * W}, {s->tries, sizeof(uint32_t) * W * P}, {s->accepts, sizeof(uint32_t) * W * P}};
+        {s->exps, sizeof(unsigned long long) * W}, {s->tries, sizeof(uint32_t) * W * P}, {s->accepts, sizeof(uint32_t) * W * P},
+        {s->sk_mom, sketch_mom_bytes(s)}, {s->sk_hist, sketch_hist_bytes(s)}};
     size_t off = kCkptHead;
     for (const Part& p : parts) {
+        if (!p.bytes) continue;
         CU(cudaMemcpyAsync(save ? (void*)(blob + off) : p.dev, save ? p.dev : (const void*)(blob + off), p.bytes,
                            cudaMemcpyDeviceToDevice, st));
         off += p.bytes;

@@ -93,6 +93,11 @@ def test_checkpoint_resume_and_adapt_flags(tmp_path):
     assert cli.main_step2([path_b, "--accept-min", "24", "--resume"] + common) == 0
     both = np.genfromtxt(os.path.join(out_b, "2_finalarray_mpi.csv"), delimiter=",")
     assert both.shape == whole.shape and np.array_equal(both[1:], whole[1:])
+    # the device-side statistics continue too: the summary of the two parts is the summary of the whole run
+    import json
+    sa = json.load(open(os.path.join(out_a, "step2_summary.json")))
+    sb = json.load(open(os.path.join(out_b, "step2_summary.json")))
+    assert sa["sep_pa_companion"] == sb["sep_pa_companion"] and sa["gelman_rubin"] == sb["gelman_rubin"]
     path_c, out_c, _ = _write_case(tmp_path, 2, tag="_adapt")
     assert cli.main_step2([path_c, "--accept-min", "40", "--adapt", "--walkers", "8", "--burn-in", "600",
                            "--seed", "21", "--stamp", "32", "--quiet"]) == 0
