@@ -102,5 +102,7 @@ def load():
 def check(rc: int):
     if rc < 0:
         msg = load().lapf_last_error().decode("utf-8", "replace")
+        if rc == -5:                                  # LAPF_ERR_SELFTEST: say which toolchain built this binary
+            msg += "\n" + (_build.build_info() or "(no build record beside the library)")
         raise LapfError("liblapf error %d: %s" % (rc, msg))
     return rc
