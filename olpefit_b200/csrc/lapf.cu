@@ -22,6 +22,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched from the driver at run time)
+
 #include "../../include/lapf.h"
 #include "lapf_device.cuh"
 
@@ -892,6 +894,51 @@ __global__ void sketch_reduce_kernel(const double* __restrict__ sk_mom, const do
         o[1] = s1;
         o[2] = s2;
         o[3] = (double)(e - b) * (double)n_rows;
+    }
+}
+
+// The same cut-out + mask + noise map with the pixels fetched by the TMA unit: a 3-D tensor map over
+// the frames [F][fy][fx] and one box of kPrepRows x nx pixels per CTA (cp.async.bulk.tensor, SASS
+// UTMALDG) -- rows of a cut-out are nx * 4 bytes long and fx * 4 bytes apart, which is exactly the
+// strided pattern a tensor map describes.  Pixels outside the frame come back as zeros from the
+// unit and are given zero weight here from their coordinates, as in frame_prep_kernel.
+constexpr int kPrepRows = 32;
+
+__global__ void __launch_bounds__(256)
+frame_prep_tma_kernel(const __grid_constant__ CUtensorMap tmap, int fy, int fx, const int32_t* __restrict__ origin,
+                      int ny, int nx, double satcut, double rn2, float* __restrict__ data_out,
+                      float* __restrict__ weight_out) {
+    extern __shared__ __align__(128) unsigned char prep_smem[];
+    __shared__ uint64_t bar;
+    float* tile = reinterpret_cast<float*>(prep_smem);
+    const int f = blockIdx.y, r0 = blockIdx.x * kPrepRows;
+    const int x0 = origin[2 * f], y0 = origin[2 * f + 1];
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&bar, (uint32_t)(kPrepRows * nx * sizeof(float)));
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_u32(tile)), "l"(&tmap), "r"(x0), "r"(y0 + r0), "r"(f), "r"(smem_u32(&bar))
+            : "memory");
+    }
+    mbar_wait(&bar, 0);
+    const int rows = min(kPrepRows, ny - r0);
+    for (int i = threadIdx.x; i < rows * nx; i += blockDim.x) {
+        const int r = i / nx, c = i % nx;
+        const int y = y0 + r0 + r, x = x0 + c;
+        float d = 0.f, w = 0.f;
+        if (y >= 0 && y < fy && x >= 0 && x < fx) {
+            const float v = tile[r * nx + c];
+            if (isfinite(v) && !((double)v > satcut)) {
+                d = v;
+                w = (float)(1.0 / (rn2 + fabs((double)v)));
+            }
+        }
+        const size_t o = ((size_t)f * ny + r0 + r) * nx + c;
+        data_out[o] = d;
+        weight_out[o] = w;
     }
 }
 
@@ -1795,6 +1842,25 @@ int lapf_write_chain_csv(const char* path, const double* rows, int64_t n_rows, i
     return ok ? LAPF_OK : fail(LAPF_ERR_INVALID, "short write to %s", path);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
 int lapf_frame_prep(const float* frames, int32_t n_frames, int32_t fy, int32_t fx, const int32_t* origin,
                     int32_t ny, int32_t nx, double satlevel, double readnoise, float* data_out,
                     float* weight_out, void* stream) {
@@ -1802,6 +1868,27 @@ int lapf_frame_prep(const float* frames, int32_t n_frames, int32_t fy, int32_t f
         return fail(LAPF_ERR_INVALID, "bad arguments to lapf_frame_prep");
     int rc = require_device();
     if (rc) return rc;
+    // Cut-outs through the TMA unit when a tensor map can describe the frames (rows 16-byte aligned, a box
+    // of at most 256 pixels a side, at most 65535 frames per launch); the plain kernel otherwise (and with
+    // LAPF_NO_TMA_PREP set).  Same arithmetic, same bits.
+    EncodeTiledFn enc = getenv("LAPF_NO_TMA_PREP") ? nullptr : encode_tiled();
+    if (enc && fx % 4 == 0 && nx % 4 == 0 && nx <= 256 && ((uintptr_t)frames & 15) == 0 && n_frames <= 65535 &&
+        (size_t)kPrepRows * nx * sizeof(float) <= 48 * 1024) {
+        alignas(64) CUtensorMap tmap;
+        const cuuint64_t dims[3] = {(cuuint64_t)fx, (cuuint64_t)fy, (cuuint64_t)n_frames};
+        const cuuint64_t strides[2] = {(cuuint64_t)fx * sizeof(float), (cuuint64_t)fx * fy * sizeof(float)};
+        const cuuint32_t box[3] = {(cuuint32_t)nx, (cuuint32_t)kPrepRows, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(frames), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            const dim3 grid((unsigned)((ny + kPrepRows - 1) / kPrepRows), (unsigned)n_frames);
+            frame_prep_tma_kernel<<<grid, 256, (size_t)kPrepRows * nx * sizeof(float), (cudaStream_t)stream>>>(
+                tmap, fy, fx, origin, ny, nx, 0.8 * satlevel, readnoise * readnoise, data_out, weight_out);
+            CU(cudaGetLastError());
+            return LAPF_OK;
+        }
+    }
     const int64_t n = (int64_t)n_frames * ny * nx;
     frame_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         frames, n_frames, fy, fx, origin, ny, nx, 0.8 * satlevel, readnoise * readnoise, data_out, weight_out);

@@ -1000,3 +1000,42 @@ def test_selftest_compares_trial_chi2_with_k1_and_restores_the_sampler(gpu, monk
         monkeypatch.delenv("LAPF_NO_SELFTEST")
         assert torch.equal(torch.cat([first, rest], dim=0), whole)
         assert torch.equal(stats_a["moments"], stats_b["moments"]) and int(stats_a["exps"]) == int(stats_b["exps"])
+
+
+def test_tma_cut_out_equals_the_plain_cut_out(gpu, monkeypatch):
+    """lapf_frame_prep fetches the cut-outs through a 3-D TMA tensor map over the frames when their
+    rows are 16-byte aligned; the plain kernel (LAPF_NO_TMA_PREP, or frames a tensor map cannot
+    describe) does the same arithmetic: identical bits, also for cut-outs that stick out of the frame,
+    masked and non-finite pixels, and sizes that are not a multiple of the box height."""
+    torch, frame = gpu["torch"], gpu["frame"]
+    rng = np.random.default_rng(4)
+    for fy, fx, size, cuts in ((200, 256, (64, 64), [(10, 20), (-7, 150), (230, -3)]),
+                               (96, 132, (40, 36), [(0, 0), (100, 60), (5, 7)]),
+                               (64, 130, (32, 32), [(3, 4), (90, 30), (0, 0)])):          # fx % 4 != 0: plain kernel both times
+        imgs = rng.normal(50.0, 40.0, (3, fy, fx)).astype(np.float32)
+        imgs[0, 30:33, 40:44] = 30000.0
+        imgs[1, 12, 13] = np.nan
+        imgs[2, 50, 60] = np.inf
+        cut = np.array(cuts, dtype=np.int32)
+        a = frame.prepare_domain(imgs, HEADER, size=size, cut=cut)
+        monkeypatch.setenv("LAPF_NO_TMA_PREP", "1")
+        b = frame.prepare_domain(imgs, HEADER, size=size, cut=cut)
+        monkeypatch.delenv("LAPF_NO_TMA_PREP")
+        assert torch.equal(a.data, b.data) and torch.equal(a.weight, b.weight)
+        # and against numpy for one frame
+        sat, rn = frame.saturation_level(HEADER), frame.read_noise(HEADER)
+        ny, nx = size
+        for f in range(3):
+            x0, y0 = cuts[f]
+            ref_d = np.zeros((ny, nx), np.float32)
+            ref_w = np.zeros((ny, nx), np.float32)
+            for r in range(ny):
+                for c in range(nx):
+                    y, x = y0 + r, x0 + c
+                    if 0 <= y < fy and 0 <= x < fx:
+                        v = imgs[f, y, x]
+                        if np.isfinite(v) and not (float(v) > 0.8 * sat):
+                            ref_d[r, c] = v
+                            ref_w[r, c] = np.float32(1.0 / (rn * rn + abs(float(v))))
+            assert np.array_equal(a.data[f].cpu().numpy(), ref_d)
+            np.testing.assert_allclose(a.weight[f].cpu().numpy(), ref_w, rtol=1e-7)

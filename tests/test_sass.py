@@ -35,6 +35,8 @@ def test_native_instructions_are_present(kernels):
         assert sum(o == "UBLKCP.S.G" for o in ops) == 2, name
         assert sum(o == "FFMA2" for o in ops) > 100 and "MUFU.EX2" in ops, name
         assert not any("MMA" in o for o in ops), name
+    prep = [v for k, v in fns.items() if "frame_prep_tma_kernel" in k]
+    assert prep and any(x.op.startswith("UTMALDG") for x in prep[0])     # the tensor-map cut-out
 
 
 def test_every_tmem_load_is_waited_for_before_its_registers_are_touched(kernels):
