@@ -898,10 +898,13 @@ __global__ void sketch_reduce_kernel(const double* __restrict__ sk_mom, const do
 }
 
 // The same cut-out + mask + noise map with the pixels fetched by the TMA unit: a 3-D tensor map over
-// the frames [F][fy][fx] and one box of kPrepRows x nx pixels per CTA (cp.async.bulk.tensor, SASS
-// UTMALDG) -- rows of a cut-out are nx * 4 bytes long and fx * 4 bytes apart, which is exactly the
-// strided pattern a tensor map describes.  Pixels outside the frame come back as zeros from the
-// unit and are given zero weight here from their coordinates, as in frame_prep_kernel.
+// the frames [F][fy][fx] and one box of kPrepRows x (nx + 4) pixels per CTA (cp.async.bulk.tensor,
+// SASS UTMALDG) -- rows of a cut-out are nx * 4 bytes long and fx * 4 bytes apart, which is exactly
+// the strided pattern a tensor map describes.  The unit wants the first byte of a box 16-byte
+// aligned (a box starting at column 10 of a float frame raises "illegal instruction", measured with
+// tools/tma_probe.cu), so the box starts at the multiple of 4 columns at or below the cut-out and is 4
+// columns wider.  Pixels outside the frame come back as zeros from the unit and are given zero
+// weight here from their coordinates, as in frame_prep_kernel.
 constexpr int kPrepRows = 32;
 
 __global__ void __launch_bounds__(256)
@@ -913,14 +916,16 @@ frame_prep_tma_kernel(const __grid_constant__ CUtensorMap tmap, int fy, int fx, 
     float* tile = reinterpret_cast<float*>(prep_smem);
     const int f = blockIdx.y, r0 = blockIdx.x * kPrepRows;
     const int x0 = origin[2 * f], y0 = origin[2 * f + 1];
+    const int xa = x0 & ~3;                       // floor to a multiple of 4, also for negative x0
+    const int bw = nx + 4, shift = x0 - xa;
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         fence_proxy_async();
-        mbar_expect_tx(&bar, (uint32_t)(kPrepRows * nx * sizeof(float)));
+        mbar_expect_tx(&bar, (uint32_t)(kPrepRows * bw * sizeof(float)));
         asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(smem_u32(tile)), "l"(&tmap), "r"(x0), "r"(y0 + r0), "r"(f), "r"(smem_u32(&bar))
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(xa), "r"(y0 + r0), "r"(f), "r"(smem_u32(&bar))
             : "memory");
     }
     mbar_wait(&bar, 0);
@@ -930,7 +935,7 @@ frame_prep_tma_kernel(const __grid_constant__ CUtensorMap tmap, int fy, int fx, 
         const int y = y0 + r0 + r, x = x0 + c;
         float d = 0.f, w = 0.f;
         if (y >= 0 && y < fy && x >= 0 && x < fx) {
-            const float v = tile[r * nx + c];
+            const float v = tile[r * bw + shift + c];
             if (isfinite(v) && !((double)v > satcut)) {
                 d = v;
                 w = (float)(1.0 / (rn2 + fabs((double)v)));
@@ -1872,18 +1877,18 @@ int lapf_frame_prep(const float* frames, int32_t n_frames, int32_t fy, int32_t f
     // of at most 256 pixels a side, at most 65535 frames per launch); the plain kernel otherwise (and with
     // LAPF_NO_TMA_PREP set).  Same arithmetic, same bits.
     EncodeTiledFn enc = getenv("LAPF_NO_TMA_PREP") ? nullptr : encode_tiled();
-    if (enc && fx % 4 == 0 && nx % 4 == 0 && nx <= 256 && ((uintptr_t)frames & 15) == 0 && n_frames <= 65535 &&
-        (size_t)kPrepRows * nx * sizeof(float) <= 48 * 1024) {
+    if (enc && fx % 4 == 0 && nx % 4 == 0 && nx + 4 <= 256 && ((uintptr_t)frames & 15) == 0 && n_frames <= 65535 &&
+        (size_t)kPrepRows * (nx + 4) * sizeof(float) <= 48 * 1024) {
         alignas(64) CUtensorMap tmap;
         const cuuint64_t dims[3] = {(cuuint64_t)fx, (cuuint64_t)fy, (cuuint64_t)n_frames};
         const cuuint64_t strides[2] = {(cuuint64_t)fx * sizeof(float), (cuuint64_t)fx * fy * sizeof(float)};
-        const cuuint32_t box[3] = {(cuuint32_t)nx, (cuuint32_t)kPrepRows, 1u};
+        const cuuint32_t box[3] = {(cuuint32_t)(nx + 4), (cuuint32_t)kPrepRows, 1u};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(frames), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
             const dim3 grid((unsigned)((ny + kPrepRows - 1) / kPrepRows), (unsigned)n_frames);
-            frame_prep_tma_kernel<<<grid, 256, (size_t)kPrepRows * nx * sizeof(float), (cudaStream_t)stream>>>(
+            frame_prep_tma_kernel<<<grid, 256, (size_t)kPrepRows * (nx + 4) * sizeof(float), (cudaStream_t)stream>>>(
                 tmap, fy, fx, origin, ny, nx, 0.8 * satlevel, readnoise * readnoise, data_out, weight_out);
             CU(cudaGetLastError());
             return LAPF_OK;
