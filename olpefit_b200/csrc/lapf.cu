@@ -317,7 +317,7 @@ __device__ __forceinline__ void record_sketch(const RunArgs& a, int wl, int fram
 // the team writes counters, chain rows and the final state.
 template <int NB, int NX, int NY, int TEAM>
 __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, const float* sw,
-                                           WarpScratch& ws, float* rt, double* team_part, int team,
+                                           WarpScratch& ws, float* rt, float* team_ct, double* team_part, int team,
                                            int tw, int wl, int frame, int lane) {
     using L = Layout<NB>;
     constexpr int P = L::P;
@@ -399,16 +399,28 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         if (a.plain) cf.fast = false;
         // in a team the update time is set by the warp with the busiest rows: culling cannot help there
         if (NX >= 64 && TEAM == 1 && a.cull) set_cull<NB, NX, NY, TEAM>(cf, lane); else no_cull<NB, NX, NY, TEAM>(cf);
+        if (TEAM > 1 && cf.fast) {
+            // the column tables of this proposal, by the whole team; the barrier at the end of the previous
+            // update (partials) lies between the last reader of the old table and these writes
+            team_consts<NB, NX, TEAM>(team_ct, cf, tw * 32 + lane);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TEAM * 32) : "memory");
+        }
         unsigned e_upd = 0;
-        double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw, &e_upd);   // :314-316
+        double chi_t = warp_chi2<NB, NX, NY, false, true, TEAM>(cf, rt, sd, sw, nullptr, lane, tw, &e_upd, 0u, team_ct);   // :314-316
         n_exps += e_upd;
         if (TEAM > 1) {
             double* slot_p = team_part + (u & 1) * TEAM;       // double-buffered: one barrier per update
             if (lane == 0) slot_p[tw] = chi_t;
             asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TEAM * 32) : "memory");
-            chi_t = 0.0;
+            // the same fixed pairwise tree in every warp of the team (depth log2 TEAM, not a chain of TEAM additions)
+            double v[TEAM];
 #pragma unroll
-            for (int t = 0; t < TEAM; ++t) chi_t += slot_p[t];  // same order in every warp of the team
+            for (int t = 0; t < TEAM; ++t) v[t] = slot_p[t];
+#pragma unroll
+            for (int h = TEAM / 2; h >= 1; h >>= 1)
+#pragma unroll
+                for (int t = 0; t < h; ++t) v[t] += v[t + h];
+            chi_t = v[0];
         }
         if (a.outside) chi_t += outside_chi2(a.outside, frame, (k == a.floor_index) ? nv : shfl_f64(p, a.floor_index));
 
@@ -496,9 +508,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
             __syncthreads();
         }
         const int team = warp / TEAM, tw = warp % TEAM;
-        if (team < a.item_count[it])
-            run_walker<NB, NX, NY, TEAM>(a, sd, sw, scratch[warp], rt + warp * Scratch<NB, NX, NY, TEAM>::FLOATS, team_part[team],
-                                         team, tw, a.walker_of[a.item_first[it] + team], f, lane);
+        if (team < a.item_count[it]) {
+            using S = Scratch<NB, NX, NY, TEAM>;
+            float* base = rt + team * (TEAM > 1 ? S::TEAM_FLOATS : S::FLOATS);
+            run_walker<NB, NX, NY, TEAM>(a, sd, sw, scratch[warp], base + (TEAM > 1 ? tw * S::TAB : 0), base + TEAM * S::TAB,
+                                         team_part[team], team, tw, a.walker_of[a.item_first[it] + team], f, lane);
+        }
     }
 }
 
@@ -1209,7 +1224,9 @@ static int configure_gibbs(lapf_sampler* s) {
     auto kern = gibbs_kernel<NB, NX, NX, NW, MINB, TEAM>;
     s->nw = NW / TEAM;   // walkers per CTA item
     s->minb = MINB;
-    constexpr size_t kBytes = 2 * sizeof(float) * NX * NX + sizeof(float) * NW * Scratch<NB, NX, NX, TEAM>::FLOATS;
+    constexpr size_t kBytes = 2 * sizeof(float) * NX * NX +
+                              sizeof(float) * (TEAM > 1 ? (NW / TEAM) * Scratch<NB, NX, NX, TEAM>::TEAM_FLOATS
+                                                        : NW * Scratch<NB, NX, NX, TEAM>::FLOATS);
     static_assert(kBytes + 16 * 1024 <= 227 * 1024, "team kernel: shared memory per CTA (dynamic + static scratch)");
     s->smem = kBytes;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));

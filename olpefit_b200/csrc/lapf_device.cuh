@@ -386,8 +386,10 @@ struct Rows {
 template <int NB, int NX, int NY, int TEAM = 1>
 struct Scratch {
     static constexpr int TAB = Rows<NY, TEAM>::NBLK * Tab<NB>::RS;
-    static constexpr int CT = 2 * NB * 2 * Geo<NX>::GPR * 4;
-    static constexpr int FLOATS = TAB + CT;
+    static constexpr int CT = 2 * NB * 2 * Geo<NX>::GPR * 4;      // column table of one panel
+    static constexpr int FLOATS = TAB + CT;                        // one warp on its own (TEAM = 1)
+    // a team: every member's block table, then ONE column table for all panels, worked out by the team together
+    static constexpr int TEAM_FLOATS = TEAM * TAB + Geo<NX>::PANELS * CT;
 };
 
 // A block's entry is 2 + K/2 independent 16-byte pieces (K/2 component pairs, 4 (class, row)
@@ -795,6 +797,38 @@ __device__ __forceinline__ void coop_consts(LaneK<NB>& lk, float* __restrict__ c
     read_consts<NB, NX>(lk, ct, cf, lane, pan);
 }
 
+// TEAM > 1: the column tables of ALL panels, once per proposal, by the whole team -- one (panel,
+// component, anchor) triple per thread.  Every member used to work out the constants of its own
+// anchor (own_consts: 8K exponentials per lane and panel, the same 16 anchors in every warp and in
+// both block rows: 32x redundant, and what kept the XU pipe busy in the team kernels); now the
+// team's 32 TEAM threads share the work and a named barrier hands the table over.  Same
+// block_consts, same inputs: same bits as coop_consts / own_consts.
+template <int NB, int NX, int TEAM>
+__device__ __forceinline__ void team_consts(float* __restrict__ ct, const Coef<NB>& cf, int tid) {
+    using G = Geo<NX>;
+    constexpr int K = 2 * NB;
+    constexpr int TASKS = G::PANELS * K * G::GPR;
+#pragma unroll
+    for (int t0 = 0; t0 < TASKS; t0 += TEAM * 32) {
+        const int t = t0 + tid;
+        if (TASKS % (TEAM * 32) == 0 || t < TASKS) {
+            const int a = t % G::GPR, kk = (t / G::GPR) % K, pan = t / (G::GPR * K);
+            float amp = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k)
+                if (kk == k) { amp = cf.amp[k]; x0 = cf.x0[k]; y0 = cf.y0[k]; }
+            const int c = kk & 1;
+            const float sa = c ? cf.sa[1] : cf.sa[0], sb = c ? cf.sb[1] : cf.sb[0], sc = c ? cf.sc[1] : cf.sc[0];
+            const float dy0 = (c ? cf.y0[1] : cf.y0[0]) - y0;
+            float4 lo, hi;
+            block_consts(amp, ((float)(pan * G::PW + 4 * a) + 1.5f) - x0, dy0, sa, sb, sc, lo, hi);
+            float4* base = reinterpret_cast<float4*>(ct) + pan * (K * 2 * G::GPR);
+            base[(kk * 2) * G::GPR + a] = lo;
+            base[(kk * 2 + 1) * G::GPR + a] = hi;
+        }
+    }
+}
+
 // The same numbers without the exchange: every lane works out the 8K constants of its own anchor
 // (4x the arithmetic, but no shared-memory round trip) -- for team members, where the latency of
 // one update is what counts.
@@ -919,7 +953,7 @@ template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1, int TM = 
 __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restrict__ scratch,
                                             const float* __restrict__ d, const float* __restrict__ w,
                                             float* __restrict__ model_out, int lane, int tw = 0,
-                                            unsigned* exps = nullptr, uint32_t tmem = 0) {
+                                            unsigned* exps = nullptr, uint32_t tmem = 0, const float* team_ct = nullptr) {
     using G = Geo<NX>;
     using T = Tab<NB>;
     using R = Rows<NY, TEAM>;
@@ -955,7 +989,8 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
             float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
             if (cf.fast) {
                 LaneK<NB> lk;
-                if (TEAM == 1) coop_consts<NB, NX>(lk, ct, cf, lane, pan); else own_consts<NB, NX>(lk, cf, lane, pan);
+                if (TEAM == 1) coop_consts<NB, NX>(lk, ct, cf, lane, pan);
+                else read_consts<NB, NX>(lk, team_ct + pan * Scratch<NB, NX, NY, TEAM>::CT, cf, lane, pan);   // team_consts wrote it
                 if (TEAM == 1) {
                     // contiguous steps: the pointers run through the segments
                     StepPtrs sp{rt + b * T::RS, d + off0, w + off0, STORE ? model_out + off0 : nullptr,
