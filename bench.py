@@ -423,7 +423,13 @@ def run_b200(a):
             consumed[j].record(compute)
             prev = streamer.run(U)
             stt = smp.stats(moments=False)
-            tot_hs[i & 1].copy_(torch.cat([stt["tries"], stt["accepts"], stt["min_tries"].reshape(1)]), non_blocking=True)
+            tot_d = torch.cat([stt["tries"], stt["accepts"], stt["min_tries"].reshape(1)])
+            # the counters leave on the copy stream too: a device->host copy queued on the compute stream would wait
+            # behind the chain rows of this batch (one copy engine per direction) and hold up the next batch
+            streamer.copy_stream.wait_stream(compute)
+            with torch.cuda.stream(streamer.copy_stream):
+                tot_hs[j].copy_(tot_d, non_blocking=True)
+            tot_d.record_stream(streamer.copy_stream)
             return 0 if prev is None else prev.shape[0]
 
         stream_step(0)                      # warm-up (allocations, first touch of the pinned buffers)
