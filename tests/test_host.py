@@ -307,3 +307,20 @@ def test_histogram_quantiles_match_numpy_percentiles():
     assert bool(torch.isnan(empty).all())
     far = np.zeros(n_bins + 2); far[-1] = 10
     assert bool(torch.isnan(stats.quantiles_from_hist(torch.tensor(far)[None], torch.tensor([centre]), torch.tensor([[width]]))).all())
+
+
+def test_frame_list_of_the_many_epoch_command_line(tmp_path):
+    """--frames LIST: one FITS path per line, relative to the list file, comments and blank lines
+    skipped, IMAGE first and never twice (cli._frame_list)."""
+    import argparse
+    from olpefit_b200 import cli
+    d = tmp_path / "night"
+    d.mkdir()
+    lst = d / "frames.txt"
+    lst.write_text("# epochs\n\nb.fits\n%s\n../night/a.fits\nc.fits\n" % (d / "c.fits"))
+    got = cli._frame_list(argparse.Namespace(image=str(d / "a.fits"), frames=str(lst)))
+    assert [os.path.basename(p) for p in got] == ["a.fits", "b.fits", "c.fits"]
+    assert cli._frame_list(argparse.Namespace(image="x.fits", frames=None)) == ["x.fits"]
+    # the new flags are additive: the reference's positional argument and -i still parse alone
+    a = cli._parser("step2").parse_args(["img.fits", "-i", "2a", "--frames", "l.txt", "--no-chains", "--chain-dtype", "f32"])
+    assert a.image == "img.fits" and a.initial_guess_option == "2a" and a.frames == "l.txt" and a.no_chains
