@@ -648,11 +648,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
     constexpr int TAB = Scratch<NB, NX, NY>::FLOATS;
     // stamps of up to 64 x 64 pixels also live in the TMEM pixel store (see tmem_fill_stamp)
     // (128 x 128: the weight plane only, the data plane is read from shared memory)
-#ifdef LAPF_EXP_NOTM   /* experiment only: pixel planes from shared memory */
-    constexpr int TM = 0;
-#else
     constexpr int TM = (Geo<NX>::PANELS == 1 && Rows<NY, 1>::HALVES == 1) ? 1 : 2;
-#endif
     constexpr uint32_t TM_COLS = TM == 1 ? 16 * (NY / Geo<NX>::RG) : 512;
     static_assert(TM_COLS >= 32 && TM_COLS <= 512 && (TM_COLS & (TM_COLS - 1)) == 0, "TMEM allocations are powers of two");
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -137,9 +137,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const float (&v)[16]) {
 // issue the load of 16 consecutive columns; the registers are valid only after tmem_ld16_wait
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t addr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-#ifdef LAPF_EXP_FUSED
-                 " tcgen05.wait::ld.sync.aligned;"
-#endif
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(addr));
@@ -398,11 +395,6 @@ struct Scratch {
 // selects): a quarter of the instructions and of the serialised MUFUs on the latency path of an
 // update.  (Whole-warp passes keep one block per lane: on 32-pixel stamps, the only case with lanes
 // to spare, the split was not faster.)
-#ifdef LAPF_EXP_BARSYNC
-#define LAPF_TABLE_SYNC() asm volatile("bar.warp.sync 0xffffffff;" ::: "memory")
-#else
-#define LAPF_TABLE_SYNC() __syncwarp()
-#endif
 template <int NB, int NX, int TR, int TEAM>
 __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Coef<NB>& cf, int lane, int row0, int tw) {
     using G = Geo<NX>;
@@ -410,12 +402,13 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
     constexpr int K = 2 * NB;
     constexpr int NQ = K / 2;                         // component pairs (narrow, wide) = objects
     constexpr int NBLK = TR / 2 / TEAM;
-#ifdef LAPF_EXP_SPLIT   /* experiment only: spread whole-warp tables over two lanes as well */
+#ifdef LAPF_EXP_SPLIT   /* experiment only: the configuration of the wrong-chi-square build of DESIGN.md 10 (whole-warp
+                           tables spread over two lanes); with the round-1 sources it reproduces the failure */
     constexpr int SPLIT = NBLK >= 32 ? 1 : (NBLK >= 16 ? 2 : (TEAM == 1 ? 2 : 4));
 #else
     constexpr int SPLIT = (TEAM == 1 || NBLK >= 32) ? 1 : (NBLK >= 16 ? 2 : 4);
 #endif
-    LAPF_TABLE_SYNC();   // readers of the previous table are done
+    __syncwarp();   // readers of the previous table are done
 #pragma unroll
     for (int j0 = 0; j0 < NBLK * SPLIT; j0 += 32) {
         const int idx = j0 + lane;
@@ -456,7 +449,7 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
             }
         }
     }
-    LAPF_TABLE_SYNC();
+    __syncwarp();
 }
 
 // Far-field culling.  |A_k| 2^(q) <= |A_k| 2^(kappa dy^2) for every pixel of a row at distance dy
