@@ -148,6 +148,52 @@ model_chi2_stamp_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t 
         chi2_out[b] = pr.outside ? chi + outside_chi2(pr.outside, f, params[b * P + pr.floor_index]) : chi;
 }
 
+// 32-pixel stamps: two vectors per warp (warp_chi2_pair), the form the batched sampler uses for
+// them, so the stateless operator and the sampler stay bit-identical.  The coefficients of a vector
+// are worked out by the first lane of its half warp (coef_from_vector: the conversions of the
+// cooperative path, one thread) and handed to the other 15 through a shared-memory image.
+template <int NB, int NX, int NY, bool STORE>
+__global__ void __launch_bounds__(128)
+model_chi2_pair_kernel(ProbPtrs pr, const double* __restrict__ params, int64_t B,
+                       const int32_t* __restrict__ frame_of, float* __restrict__ model_out,
+                       double* __restrict__ chi2_out) {
+    using L = Layout<NB>;
+    using I = CoefImg<NB, 1>;
+    constexpr int P = L::P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4;
+    const int64_t first = ((int64_t)blockIdx.x * 4 + warp) * 2;
+    if (first >= B) return;
+    const bool valid = first + h < B;                  // an odd batch: the last half warp repeats its neighbour's vector
+    const int64_t b = valid ? first + h : first;
+    const int fr = frame_of ? frame_of[b] : 0;
+    const bool frame_ok = fr >= 0 && fr < pr.n_frames;
+    const int f = frame_ok ? fr : 0;
+    __shared__ __align__(16) float img[4][2][I::STRIDE];
+    __shared__ __align__(16) float rt[4][Scratch<NB, NX, NY, 1, 2>::FLOATS];
+    if ((lane & 15) == 0) {
+        double v[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) v[j] = params[b * P + j];
+        double fl = v[2 * NB];
+#pragma unroll
+        for (int j = 2 * NB + 1; j < P; ++j) fl = (j == pr.floor_index) ? v[j] : fl;
+        Coef<NB> c0;
+        coef_from_vector<NB>(c0, v, fl, (double)pr.origin[2 * f], (double)pr.origin[2 * f + 1]);
+        set_fast_serial<NB, NX, NY>(c0);
+        if (pr.plain) c0.fast = false;
+        no_cull<NB, NX, NY>(c0);
+        store_coef<NB, 1>(img[warp][h], c0);
+    }
+    __syncwarp();
+    Coef<NB> cf;
+    load_coef<NB, 1>(cf, img[warp][h]);
+    const size_t off = (size_t)f * NX * NY;
+    const double chi = warp_chi2_pair<NB, NX, NY, STORE, false>(cf, rt[warp], pr.data + off, pr.weight + off,
+                                                                STORE ? model_out + (size_t)b * NX * NY : nullptr, lane);
+    if ((lane & 15) == 0 && valid && chi2_out)
+        chi2_out[b] = !frame_ok ? nan("") : (pr.outside ? chi + outside_chi2(pr.outside, f, params[b * P + pr.floor_index]) : chi);
+}
+
 // Any (ny, nx), e.g. the reference's whole 1024 x 1024 frame (apf_step2.py:94,237): grid =
 // (row tiles, B); per-tile FP64 partials are summed in a fixed order by reduce_tiles_kernel.
 // Centres are split into integer + fraction so pixel offsets stay accurate in FP32 at any
@@ -356,7 +402,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         if (slot == 0) {
             // lane l prepares the draws of update t0+u+l: 32 updates of random numbers at once
             const Draw dr = make_draw(a.seed, gid, (uint64_t)(a.t0 + u + lane), P);
-            const double wz = a.widths[dr.k] * dr.z;
+            const double wz = __dmul_rn(a.widths[dr.k], dr.z);    // never contracted into the sum below (lapf_device.cuh, set_shape_sc)
             __syncwarp();
             ws.k[lane] = dr.k;
             ws.step[lane] = ((a.log_mask >> dr.k) & 1u) ? exp10(wz) : wz;
@@ -368,7 +414,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         const double pk = shfl_f64(p, k);
         // proposal (apf_step2.py:63-70): additive, or multiplicative 10^(w z) for the log10
         // parameters; log10 of a negative value is nan there, and 0 stays 0.
-        const double nv = ((a.log_mask >> k) & 1u) ? (pk < 0.0 ? nan("") : pk * step) : pk + step;
+        const double nv = ((a.log_mask >> k) & 1u) ? (pk < 0.0 ? nan("") : __dmul_rn(pk, step)) : __dadd_rn(pk, step);
 
         stage_trial<NB>(ws.tf, lane, (lane == k) ? nv : p, oxd, oyd);  // :312-313
         load_centres_amps<NB>(cf, ws.tf);
@@ -528,7 +574,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
 // and at most one written per update).  The arithmetic per walker is the one of run_walker: chains
 // are bit-identical between the two forms.
 // ---------------------------------------------------------------------------------------------
-template <int NB, int NX, int NY, int LW, int TM>
+template <int NB, int NX, int NY, int LW, int TM, int WPP>
 __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, const float* sw, float* rt, float* img,
                                           int wl, int nl, int frame, int lane, uint32_t tmem) {
     using L = Layout<NB>;
@@ -554,7 +600,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
             const Draw dr = make_draw(a.seed, gid, (uint64_t)(a.t0 + u), P);   // apf_step2.py:302, :64/:68, :143
             k = dr.k;
             lnu = dr.lnu;
-            const double wz = a.widths[k] * dr.z;
+            const double wz = __dmul_rn(a.widths[k], dr.z);
             const bool is_log = (a.log_mask >> k) & 1u;
             double v[P];
 #pragma unroll
@@ -564,7 +610,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
             for (int j = 1; j < P; ++j) pk = (j == k) ? v[j] : pk;
             // proposal (apf_step2.py:63-70): additive, or multiplicative 10^(w z) for the log10
             // parameters; log10 of a negative value is nan there, and 0 stays 0.
-            nv = is_log ? (pk < 0.0 ? nan("") : pk * exp10(wz)) : pk + wz;
+            nv = is_log ? (pk < 0.0 ? nan("") : __dmul_rn(pk, exp10(wz))) : __dadd_rn(pk, wz);
 #pragma unroll
             for (int j = 0; j < P; ++j) v[j] = (j == k) ? nv : v[j];            // :312-313
             double fl = v[2 * NB];
@@ -581,13 +627,29 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
 
         // ---- passes: the warp evaluates chi-square of its walkers' trial vectors in turn --------
         double chi_t = 0.0;
+        if constexpr (WPP == 1) {
 #pragma unroll 1
-        for (int i = 0; i < nl; ++i) {
-            Coef<NB> cf;
-            load_coef<NB, Geo<NX>::PANELS>(cf, img + i * I::STRIDE);
-            unsigned e_upd = 0;
-            const double c = warp_chi2<NB, NX, NY, false, true, 1, TM>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd, tmem);   // :314-316
-            if (lane == i) { chi_t = c; n_exps += e_upd; }
+            for (int i = 0; i < nl; ++i) {
+                Coef<NB> cf;
+                load_coef<NB, Geo<NX>::PANELS>(cf, img + i * I::STRIDE);
+                unsigned e_upd = 0;
+                const double c = warp_chi2<NB, NX, NY, false, true, 1, TM>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd, tmem);   // :314-316
+                if (lane == i) { chi_t = c; n_exps += e_upd; }
+            }
+        } else {
+            // two walkers per pass: lanes 0-15 evaluate walker i, lanes 16-31 walker i + 1 (or i again, discarded)
+#pragma unroll 1
+            for (int i = 0; i < nl; i += 2) {
+                const int mine_i = min(i + (lane >> 4), nl - 1);
+                Coef<NB> cf;
+                load_coef<NB, 1>(cf, img + mine_i * I::STRIDE);
+                unsigned e_upd = 0;
+                const double c = warp_chi2_pair<NB, NX, NY, false, true, TM>(cf, rt, sd, sw, nullptr, lane, &e_upd, tmem);   // :314-316
+                const double c0 = shfl_f64(c, 0), c1 = shfl_f64(c, 16);
+                const unsigned e0 = __shfl_sync(kFull, e_upd, 0), e1 = __shfl_sync(kFull, e_upd, 16);
+                if (lane == i) { chi_t = c0; n_exps += e0; }
+                if (lane == i + 1) { chi_t = c1; n_exps += e1; }
+            }
         }
         __syncwarp();   // every pass has read its image before the next round overwrites it
 
@@ -645,11 +707,12 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
 template <int NB, int NX, int NY, int NW, int LW>
 __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_constant__ RunArgs a) {
     using I = CoefImg<NB, Geo<NX>::PANELS>;
-    constexpr int TAB = Scratch<NB, NX, NY>::FLOATS;
+    constexpr int WPP = NX == 32 ? 2 : 1;           // walkers per pass: a half warp each on 32-pixel stamps
+    constexpr int TAB = Scratch<NB, NX, NY, 1, WPP>::FLOATS;
     // stamps of up to 64 x 64 pixels also live in the TMEM pixel store (see tmem_fill_stamp)
     // (128 x 128: the weight plane only, the data plane is read from shared memory)
     constexpr int TM = (Geo<NX>::PANELS == 1 && Rows<NY, 1>::HALVES == 1) ? 1 : 2;
-    constexpr uint32_t TM_COLS = TM == 1 ? 16 * (NY / Geo<NX>::RG) : 512;
+    constexpr uint32_t TM_COLS = TM == 1 ? 16 * (NY / Geo<NX, WPP>::RG) : 512;
     static_assert(TM_COLS >= 32 && TM_COLS <= 512 && (TM_COLS & (TM_COLS - 1)) == 0, "TMEM allocations are powers of two");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
@@ -687,7 +750,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
             prep_stamp(sd, sw, NX * NY);            // (d, w) -> (d*sqrt(w), -sqrt(w)), once per staged frame
             __syncthreads();
             {
-                if constexpr (TM == 1) { if (warp < 4) tmem_fill_stamp<NX, NY>(tmem_base, sd, sw, warp, lane); }
+                if constexpr (TM == 1) { if (warp < 4) tmem_fill_stamp<NX, NY, WPP>(tmem_base, sd, sw, warp, lane); }
                 else { if (warp < 4) tmem_fill_weights<NX, NY>(tmem_base, sw, warp, lane); }
                 tmem_fence_before_sync();
                 __syncthreads();
@@ -699,7 +762,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
         const int nl = n > warp ? (n - warp + NW - 1) / NW : 0;
         const int j = warp + NW * lane;
         if (nl > 0)
-            run_batch<NB, NX, NY, LW, TM>(a, sd, sw, rt + warp * TAB, img + warp * (LW * I::STRIDE),
+            run_batch<NB, NX, NY, LW, TM, WPP>(a, sd, sw, rt + warp * TAB, img + warp * (LW * I::STRIDE),
                                           (lane < nl) ? a.walker_of[a.item_first[it] + j] : -1, nl, f, lane,
                                           tmem_base + ((uint32_t)(32 * (warp & 3)) << 16));
     }
@@ -1129,8 +1192,13 @@ static int64_t next_record_after(int64_t count, int64_t burn_in, int thin) {
 template <int NB, int NX, bool STORE>
 static void launch_stamp_k1(const ProbPtrs& pr, const double* params, int64_t B, const int32_t* frame_of,
                             float* model_out, double* chi2_out, cudaStream_t st) {
-    const unsigned grid = (unsigned)((B + 3) / 4);
-    model_chi2_stamp_kernel<NB, NX, NX, STORE><<<grid, 128, 0, st>>>(pr, params, B, frame_of, model_out, chi2_out);
+    if constexpr (NX == 32) {
+        const unsigned grid = (unsigned)((B + 7) / 8);          // two vectors per warp, four warps per CTA
+        model_chi2_pair_kernel<NB, NX, NX, STORE><<<grid, 128, 0, st>>>(pr, params, B, frame_of, model_out, chi2_out);
+    } else {
+        const unsigned grid = (unsigned)((B + 3) / 4);
+        model_chi2_stamp_kernel<NB, NX, NX, STORE><<<grid, 128, 0, st>>>(pr, params, B, frame_of, model_out, chi2_out);
+    }
 }
 
 template <int NB, int NX>
@@ -1248,7 +1316,8 @@ static int configure_batch(lapf_sampler* s) {
     s->nw = NW;
     s->chunk = NW * LW;
     s->minb = 1;
-    constexpr size_t kBytes = sizeof(float) * (2 * NX * NX + NW * Scratch<NB, NX, NX>::FLOATS + NW * LW * CoefImg<NB, Geo<NX>::PANELS>::STRIDE);
+    constexpr size_t kBytes = sizeof(float) * (2 * NX * NX + NW * Scratch<NB, NX, NX, 1, (NX == 32 ? 2 : 1)>::FLOATS +
+                                               NW * LW * CoefImg<NB, Geo<NX>::PANELS>::STRIDE);
     static_assert(kBytes + 256 <= 227 * 1024, "batched kernel: shared memory per CTA");
     s->smem = kBytes;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
@@ -1713,6 +1782,21 @@ int lapf_sampler_selftest(lapf_sampler* s, void* stream) {
     rc = lapf_sampler_load(s, blob, (int64_t)blob_bytes, st);      // synchronises the stream: `init` and `res` are settled
     if (rc) { cleanup(); return rc; }
     CUT(cudaStreamSynchronize(st));
+    if (const char* path = getenv("LAPF_SELFTEST_DUMP")) {
+        // diagnosis of a failing build: [U, W, P] as int64, then probe [U W 3], chi [U W], trials [U W P] as doubles
+        std::vector<double> hp((size_t)n * 3), hc((size_t)n), ht((size_t)n * P);
+        CUT(cudaMemcpy(hp.data(), probe, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost));
+        CUT(cudaMemcpy(hc.data(), chi, sizeof(double) * hc.size(), cudaMemcpyDeviceToHost));
+        CUT(cudaMemcpy(ht.data(), trials, sizeof(double) * ht.size(), cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(path, "wb")) {
+            const int64_t head[3] = {U, W, P};
+            fwrite(head, sizeof(int64_t), 3, f);
+            fwrite(hp.data(), sizeof(double), hp.size(), f);
+            fwrite(hc.data(), sizeof(double), hc.size(), f);
+            fwrite(ht.data(), sizeof(double), ht.size(), f);
+            fclose(f);
+        }
+    }
     cleanup();
 #undef CUT
     s->launches += 3;

@@ -184,12 +184,20 @@ struct Coef {
 
 // a, b, c of astropy Gaussian2D.evaluate, pre-scaled so that the
 // exponential is a bare ex2:  G = A * 2^(sa*dx^2 + sb*dx*dy + sc*dy^2).
+//
+// Coefficients, the safe-range test and the culling bounds are inlined into several kernels (the
+// stateless operator, the team sampler, the batched sampler), whose chi-squares must agree bit for
+// bit.  Plain `a * b + c` leaves it to the compiler whether to contract into an FMA, and it decides
+// per inlined copy (a build of the two-vectors-per-pass operator contracted `a - a * ratio` in one
+// kernel only: 1.5 % of the trial chi-squares differed in the last bits).  So every sum of products
+// here is spelled with rounding intrinsics, which are never contracted.
 template <int NB>
 __device__ __forceinline__ void set_shape_sc(Coef<NB>& cf, int which, float sx, float sy, float s, float c) {
-    const float ivx = 1.0f / (sx * sx), ivy = 1.0f / (sy * sy);
-    cf.sa[which] = -0.5f * kLog2e * (c * c * ivx + s * s * ivy);
-    cf.sb[which] = -kLog2e * (s * c) * (ivx - ivy);     // sin(2t)/2 = s*c
-    cf.sc[which] = -0.5f * kLog2e * (s * s * ivx + c * c * ivy);
+    const float ivx = __fdiv_rn(1.0f, __fmul_rn(sx, sx)), ivy = __fdiv_rn(1.0f, __fmul_rn(sy, sy));
+    const float cc = __fmul_rn(c, c), ss = __fmul_rn(s, s);
+    cf.sa[which] = __fmul_rn(-0.5f * kLog2e, __fmaf_rn(cc, ivx, __fmul_rn(ss, ivy)));
+    cf.sb[which] = __fmul_rn(__fmul_rn(-kLog2e, __fmul_rn(s, c)), __fsub_rn(ivx, ivy));     // sin(2t)/2 = s*c
+    cf.sc[which] = __fmul_rn(-0.5f * kLog2e, __fmaf_rn(ss, ivx, __fmul_rn(cc, ivy)));
 }
 
 template <int NB>
@@ -231,9 +239,9 @@ __device__ __forceinline__ void load_centres_amps(Coef<NB>& cf, const float* tf)
         cf.y0[2 * o] = tf[2 * o + 1];
         cf.x0[2 * o + 1] = tf[L::P + 2 * o];
         cf.y0[2 * o + 1] = tf[L::P + 2 * o + 1];
-        const float a = tf[L::I_AMP + o] - bkgd;          // :95
-        const float aw = a * ratio;                       // :96
-        cf.amp[2 * o] = a - aw;                           // :97
+        const float a = __fsub_rn(tf[L::I_AMP + o], bkgd);   // :95
+        const float aw = __fmul_rn(a, ratio);                // :96
+        cf.amp[2 * o] = __fsub_rn(a, aw);                    // :97 (two roundings, never an FMA: see set_shape_sc)
         cf.amp[2 * o + 1] = aw;
     }
 }
@@ -338,14 +346,20 @@ __device__ __forceinline__ void coef_from_vector(Coef<NB>& cf, const double (&v)
 // per plane (16 lanes read 256 contiguous bytes of a row: conflict-free).  The column offsets of a
 // lane never change, so everything that depends on them lives in registers for the whole panel.
 // ---------------------------------------------------------------------------------------------
-template <int NX>
+// WPP = 2 (32-pixel stamps, whole-warp passes): TWO parameter vectors per pass, one per half warp.  A
+// 32-pixel row needs only 8 column anchors, so a half warp (8 anchors x 2 block rows, 4 rows per
+// warp step, 8 steps) covers the stamp, and everything a pass does once -- coefficient load, block
+// table (which leaves 16 lanes idle otherwise), reduction, loop control -- serves two walkers.
+template <int NX, int WPP = 1>
 struct Geo {
     static constexpr int PW = NX >= 64 ? 64 : 32;
     static constexpr int PANELS = NX / PW;
     static constexpr int GPR = PW / 4;        // 4-pixel column groups across a panel: 16 / 8
-    static constexpr int BPS = 32 / GPR;      // 2-row blocks per warp step: 2 / 4
-    static constexpr int RG = 2 * BPS;        // rows per warp step: 4 / 8
+    static constexpr int LPW = 32 / WPP;      // lanes that work on one parameter vector
+    static constexpr int BPS = LPW / GPR;     // 2-row blocks per warp step: 2 / 4 (2 with two vectors per pass)
+    static constexpr int RG = 2 * BPS;        // rows per warp step: 4 / 8 (4)
     static_assert(NX % PW == 0 && (NX == 32 || NX % 64 == 0), "unsupported stamp width");
+    static_assert(WPP == 1 || (WPP == 2 && NX == 32), "two vectors per pass: 32-pixel stamps only");
 };
 
 // Block table: everything that depends on the rows only, computed ONCE per proposal by the warp
@@ -380,11 +394,14 @@ struct Rows {
 
 // per-warp shared-memory scratch of the pixel loop: the block table, then the column table
 // (coop_consts: [component][row of the block][anchor][4 column offsets])
-template <int NB, int NX, int NY, int TEAM = 1>
+template <int NB, int NX, int NY, int TEAM = 1, int WPP = 1>
 struct Scratch {
-    static constexpr int TAB = Rows<NY, TEAM>::NBLK * Tab<NB>::RS;
-    static constexpr int CT = 2 * NB * 2 * Geo<NX>::GPR * 4;      // column table of one panel
-    static constexpr int FLOATS = TAB + CT;                        // one warp on its own (TEAM = 1)
+    // block table of one vector (two vectors per pass: 8 floats apart in the banks, so the four blocks
+    // a warp step reads -- 2 block rows x 2 vectors -- are one conflict-free wavefront)
+    static constexpr int TAB1 = Rows<NY, TEAM>::NBLK * Tab<NB>::RS + (WPP > 1 ? 8 : 0);
+    static constexpr int TAB = WPP * TAB1;
+    static constexpr int CT = 2 * NB * 2 * Geo<NX>::GPR * 4;      // column table of one panel and vector
+    static constexpr int FLOATS = TAB + WPP * CT;                  // one warp on its own (TEAM = 1)
     // a team: every member's block table, then ONE column table for all panels, worked out by the team together
     static constexpr int TEAM_FLOATS = TEAM * TAB + Geo<NX>::PANELS * CT;
 };
@@ -395,9 +412,9 @@ struct Scratch {
 // selects): a quarter of the instructions and of the serialised MUFUs on the latency path of an
 // update.  (Whole-warp passes keep one block per lane: on 32-pixel stamps, the only case with lanes
 // to spare, the split was not faster.)
-template <int NB, int NX, int TR, int TEAM>
+template <int NB, int NX, int TR, int TEAM, int WPP = 1>
 __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Coef<NB>& cf, int lane, int row0, int tw) {
-    using G = Geo<NX>;
+    using G = Geo<NX, WPP>;
     using T = Tab<NB>;
     constexpr int K = 2 * NB;
     constexpr int NQ = K / 2;                         // component pairs (narrow, wide) = objects
@@ -409,10 +426,11 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
     constexpr int SPLIT = (TEAM == 1 || NBLK >= 32) ? 1 : (NBLK >= 16 ? 2 : 4);
 #endif
     __syncwarp();   // readers of the previous table are done
+    if (WPP > 1) rt += (lane / G::LPW) * (NBLK * T::RS + 8);      // the table of this half warp's vector (Scratch::TAB1)
 #pragma unroll
-    for (int j0 = 0; j0 < NBLK * SPLIT; j0 += 32) {
-        const int idx = j0 + lane;
-        if ((NBLK * SPLIT) % 32 == 0 || idx < NBLK * SPLIT) {
+    for (int j0 = 0; j0 < NBLK * SPLIT; j0 += G::LPW) {
+        const int idx = j0 + lane % G::LPW;
+        if ((NBLK * SPLIT) % G::LPW == 0 || idx < NBLK * SPLIT) {
             const int jb = idx / SPLIT, part = idx % SPLIT;   // local block: warp step jb / BPS of this warp, block jb % BPS
             const int step = (jb / G::BPS) * TEAM + tw;
             const float yb = (float)(row0 + step * G::RG + 2 * (jb % G::BPS)) + 0.5f;
@@ -426,8 +444,9 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
 #pragma unroll
                     for (int t = 1; t < SPLIT; ++t)
                         if (q0 + t < NQ && part == t) { y0a = cf.y0[2 * (q0 + t)]; y0b = cf.y0[2 * (q0 + t) + 1]; }
-                    const float yda = yb - y0a, ydb = yb - y0b;
-                    o[q] = make_float4(cf.sb[0] * yda, (cf.sc[0] * yda) * yda, cf.sb[1] * ydb, (cf.sc[1] * ydb) * ydb);
+                    const float yda = __fsub_rn(yb, y0a), ydb = __fsub_rn(yb, y0b);
+                    o[q] = make_float4(__fmul_rn(cf.sb[0], yda), __fmul_rn(__fmul_rn(cf.sc[0], yda), yda),
+                                       __fmul_rn(cf.sb[1], ydb), __fmul_rn(__fmul_rn(cf.sc[1], ydb), ydb));
                 }
             }
             // factor quadruples pr = 2 c + ii = part, part + SPLIT, ...
@@ -437,12 +456,12 @@ __device__ __forceinline__ void build_row_table(float* __restrict__ rt, const Co
                 const int pr = p0 + part;
                 const bool c = (pr >> 1) != 0, hi = (pr & 1) != 0;
                 const float sbc = c ? cf.sb[1] : cf.sb[0], scc = c ? cf.sc[1] : cf.sc[0];
-                const float yd = yb - (c ? cf.y0[1] : cf.y0[0]);
-                const float p = sbc * yd;                       // sb_c * dyb_c
-                const float sy = (scc * yd) * 2.f;
-                const float g = 0.25f * scc;
+                const float yd = __fsub_rn(yb, c ? cf.y0[1] : cf.y0[0]);
+                const float p = __fmul_rn(sbc, yd);             // sb_c * dyb_c
+                const float sy = __fmul_rn(__fmul_rn(scc, yd), 2.f);
+                const float g = __fmul_rn(0.25f, scc);
                 const float i = hi ? 0.5f : -0.5f;
-                const float pj = fmaf(i, sbc, p), base = fmaf(i, sy, g);
+                const float pj = __fmaf_rn(i, sbc, p), base = __fmaf_rn(i, sy, g);
                 const float2 pj2 = make_float2(pj, pj), b2 = make_float2(base, base);
                 const float2 alo = __ffma2_rn(jlo, pj2, b2), ahi = __ffma2_rn(jhi, pj2, b2);
                 o[T::OFF_T / 4 + pr] = make_float4(ex2_approx(alo.x), ex2_approx(alo.y), ex2_approx(ahi.x), ex2_approx(ahi.y));
@@ -471,25 +490,27 @@ __device__ __forceinline__ void cull_one(float a, float x0, float y0, float sa, 
     constexpr int STEPS = NY / G::RG;
     constexpr uint32_t kAllPans = (1u << G::PANELS) - 1u;
     // approximate log2 / divide / sqrt are fine here: the radius gets a whole pixel of slack
-    const float tau = 0x1p-27f * fabsf(floor_v);
+    const float tau = __fmul_rn(0x1p-27f, fabsf(floor_v));
     const float L = __log2f(__fdividef(fabsf(a), tau));    // bits of headroom above tau
     lo = 0; hi = STEPS - 1;                                // default: everything (also for nan / inf)
     pm = kAllPans;
     if (L <= 0.f) {                                        // below tau everywhere
         lo = STEPS; hi = -1; pm = 0u;
     } else {
-        const float ky = sc - __fdividef(sb * sb, 4.f * sa), kx = sa - __fdividef(sb * sb, 4.f * sc);   // both < 0
-        const float Y = __fsqrt_rn(__fdividef(L, -ky)) + 1.f, X = __fsqrt_rn(__fdividef(L, -kx)) + 1.f;
+        const float sb2 = __fmul_rn(sb, sb);
+        const float ky = __fsub_rn(sc, __fdividef(sb2, __fmul_rn(4.f, sa))), kx = __fsub_rn(sa, __fdividef(sb2, __fmul_rn(4.f, sc)));   // both < 0
+        const float Y = __fadd_rn(__fsqrt_rn(__fdividef(L, -ky)), 1.f), X = __fadd_rn(__fsqrt_rn(__fdividef(L, -kx)), 1.f);
         if (Y < 1e6f && fabsf(y0) < 1e6f) {
-            lo = max(0, (int)ceilf((y0 - Y - (float)(G::RG - 1)) / (float)G::RG));
-            hi = min(STEPS - 1, (int)floorf((y0 + Y) / (float)G::RG));
+            constexpr float kInvRG = 1.f / (float)G::RG;       // a power of two
+            lo = max(0, (int)ceilf(__fmul_rn(__fsub_rn(__fsub_rn(y0, Y), (float)(G::RG - 1)), kInvRG)));
+            hi = min(STEPS - 1, (int)floorf(__fmul_rn(__fadd_rn(y0, Y), kInvRG)));
             if (lo > hi) { lo = STEPS; hi = -1; }
         }
         if (G::PANELS > 1 && X < 1e6f && fabsf(x0) < 1e6f) {
             pm = 0u;
 #pragma unroll
             for (int p = 0; p < G::PANELS; ++p)
-                if (x0 + X >= (float)(p * G::PW) && x0 - X <= (float)(p * G::PW + G::PW - 1)) pm |= 1u << p;
+                if (__fadd_rn(x0, X) >= (float)(p * G::PW) && __fsub_rn(x0, X) <= (float)(p * G::PW + G::PW - 1)) pm |= 1u << p;
         }
     }
 }
@@ -590,13 +611,17 @@ __device__ __forceinline__ void no_cull(Coef<NB>& cf) {
 template <int NX, int NY>
 __device__ __forceinline__ bool fast_one(float a, float x0, float y0, float yref, float sa, float sb, float sc,
                                          float floor_v) {
-    const float dxm = fabsf(x0 - 0.5f * NX) + 0.5f * NX;      // >= |anchor - x0| for every anchor column
-    const float dym = fabsf(yref - 0.5f * NY) + 0.5f * NY;    // >= |block centre - y0_c| for every block
-    const float dy0 = fabsf(yref - y0);
-    const float argc = 1.5f * (fabsf(sa) * (2.f * dxm + 1.5f) + fabsf(sb) * dy0) + 0.5f * (fabsf(sb) * dxm + 2.f * fabsf(sc) * dy0);
-    const float argt = 1.5f * fabsf(sb) * (dym + 0.5f) + fabsf(sc) * (dym + 0.25f);
-    return argc <= 40.f && argt <= 40.f && fabsf(sc) <= 1e30f &&
-           fabsf(a) <= 0x1p21f * fabsf(floor_v) && fabsf(a) <= 1e12f;    // all false on nan
+    const float dxm = __fadd_rn(fabsf(__fsub_rn(x0, 0.5f * NX)), 0.5f * NX);      // >= |anchor - x0| for every anchor column
+    const float dym = __fadd_rn(fabsf(__fsub_rn(yref, 0.5f * NY)), 0.5f * NY);    // >= |block centre - y0_c| for every block
+    const float dy0 = fabsf(__fsub_rn(yref, y0));
+    const float asa = fabsf(sa), asb = fabsf(sb), asc = fabsf(sc);
+    // argc = 1.5 (|sa| (2 dxm + 1.5) + |sb| dy0) + 0.5 (|sb| dxm + 2 |sc| dy0);  argt = 1.5 |sb| (dym + 0.5) + |sc| (dym + 0.25)
+    const float c1 = __fmaf_rn(asa, __fmaf_rn(2.f, dxm, 1.5f), __fmul_rn(asb, dy0));
+    const float c2 = __fmaf_rn(asb, dxm, __fmul_rn(__fmul_rn(2.f, asc), dy0));
+    const float argc = __fmaf_rn(1.5f, c1, __fmul_rn(0.5f, c2));
+    const float argt = __fmaf_rn(__fmul_rn(1.5f, asb), __fadd_rn(dym, 0.5f), __fmul_rn(asc, __fadd_rn(dym, 0.25f)));
+    return argc <= 40.f && argt <= 40.f && asc <= 1e30f &&
+           fabsf(a) <= __fmul_rn(0x1p21f, fabsf(floor_v)) && fabsf(a) <= 1e12f;    // all false on nan
 }
 
 template <int NB, int NX, int NY>
@@ -642,8 +667,9 @@ struct StepPtrs {          // where the next warp step of this lane lives
 // store) -> residuals -> chi-square accumulators
 template <int NX, bool STORE, bool PREP>
 __device__ __forceinline__ void finish_step(const float2 (&m)[4], const float4& d0, const float4& d1,
-                                            const float4& w0, const float4& w1, float* mp, float2& s0, float2& s1) {
-    if (STORE) {
+                                            const float4& w0, const float4& w1, float* mp, float2& s0, float2& s1,
+                                            bool keep = true) {
+    if (STORE && keep) {
         *reinterpret_cast<float4*>(mp) = make_float4(m[0].x, m[0].y, m[1].x, m[1].y);
         *reinterpret_cast<float4*>(mp + NX) = make_float4(m[2].x, m[2].y, m[3].x, m[3].y);
     }
@@ -674,10 +700,10 @@ __device__ __forceinline__ void finish_step(const float2 (&m)[4], const float4& 
 // coefficients as broadcast operands) -- 3 FFMA2 + 2 MUFU.EX2 per pixel PAIR and component:
 // SFU-bound.  Kept for parameter vectors set_fast turns away; it takes no table (the row terms are
 // worked out per row on the spot).
-template <int NB, int NX, int NY, bool STORE, bool PREP>
+template <int NB, int NX, int NY, bool STORE, bool PREP, int WPP = 1>
 __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)[2 * NB][2], float2& s0, float2& s1,
-                                          int& i, int i1, StepPtrs& sp) {
-    using G = Geo<NX>;
+                                          int& i, int i1, StepPtrs& sp, bool keep = true) {
+    using G = Geo<NX, WPP>;
     constexpr int K = 2 * NB;
     const float* dp = sp.dp;
     const float* wp = sp.wp;
@@ -698,8 +724,8 @@ __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)
             const float2 am2 = make_float2(cf.amp[k], cf.amp[k]);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const float yd = (row + (float)r) - cf.y0[k];
-                const float by = cf.sb[k & 1] * yd, cy = (cf.sc[k & 1] * yd) * yd;
+                const float yd = __fsub_rn(__fadd_rn(row, (float)r), cf.y0[k]);
+                const float by = __fmul_rn(cf.sb[k & 1], yd), cy = __fmul_rn(__fmul_rn(cf.sc[k & 1], yd), yd);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const float2 t = __ffma2_rn(sa2, xd[k][j], make_float2(by, by));
@@ -709,7 +735,7 @@ __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)
                 }
             }
         }
-        finish_step<NX, STORE, PREP>(m, d0, d1, w0, w1, mp, s0, s1);
+        finish_step<NX, STORE, PREP>(m, d0, d1, w0, w1, mp, s0, s1, keep);
         if (STORE) mp += G::RG * NX;
         dp += G::RG * NX;
         wp += G::RG * NX;
@@ -744,8 +770,8 @@ struct LaneK {
 // i = -1/2 (lo) and +1/2 (hi), columns j = -3/2, -1/2, 1/2, 3/2.
 __device__ __forceinline__ void block_consts(float amp, float dxa, float dy0, float sa, float sb, float sc,
                                              float4& lo, float4& hi) {
-    const float u = sb * dy0, d2 = 2.f * dxa;
-    const float v = fmaf(sb, dxa, 2.f * (sc * dy0));
+    const float u = __fmul_rn(sb, dy0), d2 = __fmul_rn(2.f, dxa);
+    const float v = __fmaf_rn(sb, dxa, __fmul_rn(2.f, __fmul_rn(sc, dy0)));
     const float2 u2 = make_float2(u, u), sa2 = make_float2(sa, sa), d22 = make_float2(d2, d2);
     const float2 jlo = make_float2(-1.5f, -0.5f), jhi = make_float2(0.5f, 1.5f);
     const float2 xlo = __fmul2_rn(jlo, __ffma2_rn(sa2, __fadd2_rn(d22, jlo), u2));
@@ -753,8 +779,10 @@ __device__ __forceinline__ void block_consts(float amp, float dxa, float dy0, fl
     const float hv = 0.5f * v;
     const float2 m2 = make_float2(-hv, -hv), p2 = make_float2(hv, hv);
     const float2 a0 = __fadd2_rn(xlo, m2), a1 = __fadd2_rn(xhi, m2), b0 = __fadd2_rn(xlo, p2), b1 = __fadd2_rn(xhi, p2);
-    lo = make_float4(amp * ex2_approx(a0.x), amp * ex2_approx(a0.y), amp * ex2_approx(a1.x), amp * ex2_approx(a1.y));
-    hi = make_float4(amp * ex2_approx(b0.x), amp * ex2_approx(b0.y), amp * ex2_approx(b1.x), amp * ex2_approx(b1.y));
+    lo = make_float4(__fmul_rn(amp, ex2_approx(a0.x)), __fmul_rn(amp, ex2_approx(a0.y)), __fmul_rn(amp, ex2_approx(a1.x)),
+                     __fmul_rn(amp, ex2_approx(a1.y)));
+    hi = make_float4(__fmul_rn(amp, ex2_approx(b0.x)), __fmul_rn(amp, ex2_approx(b0.y)), __fmul_rn(amp, ex2_approx(b1.x)),
+                     __fmul_rn(amp, ex2_approx(b1.y)));
 }
 
 template <int NB, int NX>
@@ -763,15 +791,16 @@ __device__ __forceinline__ void read_consts(LaneK<NB>& lk, const float* __restri
 // The C_k,ij of the GPR anchors of a panel (columns 4a + 1.5), worked out once per proposal by the
 // warp -- one (anchor, component) pair per lane and round -- and handed round through the column
 // table ct[k][row of the block][a][4]; every lane then reads the 8K values of its own anchor.
-template <int NB, int NX>
+template <int NB, int NX, int WPP = 1>
 __device__ __forceinline__ void coop_consts(LaneK<NB>& lk, float* __restrict__ ct, const Coef<NB>& cf, int lane, int pan) {
-    using G = Geo<NX>;
+    using G = Geo<NX, WPP>;
     constexpr int K = 2 * NB;
     __syncwarp();   // readers of the previous column table are done
+    if (WPP > 1) ct += (lane / G::LPW) * (K * 2 * G::GPR * 4);     // the table of this half warp's vector (Scratch::CT)
 #pragma unroll
-    for (int t0 = 0; t0 < G::GPR * K; t0 += 32) {
-        const int t = t0 + lane;
-        if ((G::GPR * K) % 32 == 0 || t < G::GPR * K) {
+    for (int t0 = 0; t0 < G::GPR * K; t0 += G::LPW) {
+        const int t = t0 + lane % G::LPW;
+        if ((G::GPR * K) % G::LPW == 0 || t < G::GPR * K) {
             const int a = t % G::GPR, kk = t / G::GPR;
             float amp = cf.amp[0], x0 = cf.x0[0], y0 = cf.y0[0];
 #pragma unroll
@@ -859,10 +888,10 @@ __device__ __forceinline__ void read_consts(LaneK<NB>& lk, const float* __restri
     }
 }
 
-template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND, int TM = 0>
+template <int NB, int NX, int NY, bool STORE, bool PREP, int KIND, int TM = 0, int WPP = 1>
 __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<NB>& lk, float2& s0, float2& s1,
-                                               int& i, int i1, StepPtrs& sp) {
-    using G = Geo<NX>;
+                                               int& i, int i1, StepPtrs& sp, bool keep = true) {
+    using G = Geo<NX, WPP>;
     using T = Tab<NB>;
     constexpr int K = 2 * NB;
     const float* rp = sp.rp;
@@ -904,7 +933,7 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
 #pragma unroll
                 for (int o = 0; o < NB; ++o) {
                     const int k = 2 * o + c;
-                    const float q = fmaf(lk.dxa[k], fmaf(cf.sa[c], lk.dxa[k], rc[2 * k]), rc[2 * k + 1]);
+                    const float q = __fmaf_rn(lk.dxa[k], __fmaf_rn(cf.sa[c], lk.dxa[k], rc[2 * k]), rc[2 * k + 1]);
                     const float e = ex2_approx(q);
                     const float2 e2 = make_float2(e, e);
 #pragma unroll
@@ -928,7 +957,7 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
             w0 = make_float4(__uint_as_float(tv[8]), __uint_as_float(tv[9]), __uint_as_float(tv[10]), __uint_as_float(tv[11]));
             w1 = make_float4(__uint_as_float(tv[12]), __uint_as_float(tv[13]), __uint_as_float(tv[14]), __uint_as_float(tv[15]));
         }
-        finish_step<NX, STORE, PREP>(m, d0, d1, w0, w1, mp, s0, s1);
+        finish_step<NX, STORE, PREP>(m, d0, d1, w0, w1, mp, s0, s1, keep);
         if (STORE) mp += G::RG * NX;
         rp += G::BPS * T::RS;
         dp += G::RG * NX;
@@ -1037,15 +1066,76 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
     return warp_sum_f64(acc);
 }
 
+// Two parameter vectors per pass on a 32-pixel stamp (Geo<NX, 2>): every lane holds the coefficients
+// of ITS half warp's vector; tables, lane constants, loop and reduction are shared instruction
+// streams.  Returns, in every lane, chi-square of the vector of the lane's half warp.  A vector
+// outside the safe range of the factorised loop (set_fast) takes the plain loop as it would alone:
+// if the two halves disagree both loops run and each half keeps its own result, so chi-square and
+// model image stay pure functions of the vector, whatever it is paired with.
+template <int NB, int NX, int NY, bool STORE, bool PREP, int TM = 0>
+__device__ __forceinline__ double warp_chi2_pair(const Coef<NB>& cf, float* __restrict__ scratch,
+                                                 const float* __restrict__ d, const float* __restrict__ w,
+                                                 float* __restrict__ model_out, int lane, unsigned* exps = nullptr,
+                                                 uint32_t tmem = 0) {
+    using G = Geo<NX, 2>;
+    using T = Tab<NB>;
+    using S = Scratch<NB, NX, NY, 1, 2>;
+    constexpr int K = 2 * NB;
+    constexpr int STEPS = NY / G::RG;
+    static_assert(NX == 32 && NY == 32 && G::PANELS == 1, "two vectors per pass: 32 x 32 stamps");
+    static_assert(TM == 0 || PREP, "the TMEM pixel store holds prepared stamps");
+    const int wl = lane % G::LPW, h = lane / G::LPW, a = wl % G::GPR, b = wl / G::GPR;
+    float* rt = scratch;
+    float* ct = scratch + S::TAB;
+    if (exps) *exps += cf.nexp;
+    const bool run_fast = __any_sync(kFull, cf.fast), run_plain = __any_sync(kFull, !cf.fast);
+    const int off0 = (2 * b) * NX + 4 * a;        // the lane's block of warp step 0
+    float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+    if (run_fast) {
+        build_row_table<NB, NX, NY, 1, 2>(rt, cf, lane, 0, 0);
+        LaneK<NB> lk;
+        coop_consts<NB, NX, 2>(lk, ct, cf, lane, 0);
+        float2 f0 = make_float2(0.f, 0.f), f1 = make_float2(0.f, 0.f);
+        StepPtrs sp{rt + h * S::TAB1 + b * T::RS, d + off0, w + off0, STORE ? model_out + off0 : nullptr, tmem, 0.f};
+        int i = 0;
+        row_steps_fast<NB, NX, NY, STORE, PREP, 2, TM, 2>(cf, lk, f0, f1, i, STEPS, sp, cf.fast);
+        if (cf.fast) { s0 = f0; s1 = f1; }
+    }
+    if (run_plain) {
+        float2 xd[K][2];
+        const float fa = (float)(4 * a);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float2 nx0 = make_float2(-cf.x0[k], -cf.x0[k]);
+            xd[k][0] = __fadd2_rn(make_float2(fa, fa + 1.f), nx0);
+            xd[k][1] = __fadd2_rn(make_float2(fa + 2.f, fa + 3.f), nx0);
+        }
+        float2 p0 = make_float2(0.f, 0.f), p1 = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int st = 0; st < STEPS; ++st) {
+            const int so = st * G::RG * NX;
+            StepPtrs sp{nullptr, d + off0 + so, w + off0 + so, STORE ? model_out + off0 + so : nullptr, 0u,
+                        (float)(st * G::RG + 2 * b)};
+            int i = 0;
+            row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, p0, p1, i, 1, sp, !cf.fast);
+        }
+        if (!cf.fast) { s0 = p0; s1 = p1; }
+    }
+    double acc = (double)((s0.x + s0.y) + (s1.x + s1.y));
+#pragma unroll
+    for (int off = G::LPW / 2; off >= 1; off >>= 1) acc += shfl_xor_f64(acc, off);     // within the half warp
+    return acc;
+}
+
 // Copy of the prepared stamp into the TMEM pixel store: called by warps 0..3 (one per TMEM lane
 // quadrant) after prep_stamp; warp step i of the lane goes to columns 16 i .. 16 i + 15 in the
 // order the loop consumes them (data row 0, data row 1, weight row 0, weight row 1).
-template <int NX, int NY>
+template <int NX, int NY, int WPP = 1>
 __device__ __forceinline__ void tmem_fill_stamp(uint32_t tmem_base, const float* __restrict__ sd,
                                                 const float* __restrict__ sw, int warp, int lane) {
-    using G = Geo<NX>;
+    using G = Geo<NX, WPP>;
     static_assert(G::PANELS == 1, "one panel");
-    const int a = lane % G::GPR, b = lane / G::GPR;
+    const int a = (lane % G::LPW) % G::GPR, b = (lane % G::LPW) / G::GPR;      // both half warps hold the same pixels
     const uint32_t addr = tmem_base + ((uint32_t)(32 * warp) << 16);
 #pragma unroll 1
     for (int i = 0; i < NY / G::RG; ++i) {
