@@ -708,6 +708,63 @@ def test_wild_vectors_leave_the_factorised_loop(gpu):
     assert gpu["torch"].equal(res[0], res[1])
 
 
+@pytest.mark.parametrize("nbody", [2, 3])
+def test_two_vectors_per_pass_are_independent_of_their_partner(gpu, nbody):
+    """32-pixel stamps are evaluated two vectors per pass, one per half warp.
+    Chi-square and the model image must stay pure functions of the vector: alone (a batch of one),
+    in an odd batch, paired with a tame or with a wild partner (which takes the plain loop, so both
+    loops run in that pass), in either half of the warp -- always the same bits, and always the
+    float64 oracle to the stated tolerance."""
+    synth = gpu["synth"]
+    lay = orc.layout_for(nbody)
+    size = 32
+    ox, oy = synth.stamp_origin(size)
+    img, truth = synth.make_frame(8, nbody, region=(oy, oy + size, ox, ox + size))
+    dom = _domain(gpu, img, (ox, oy), nbody)
+    tl = truth.copy()
+    tl[0:2 * nbody:2] -= ox
+    tl[1:2 * nbody:2] -= oy
+    tame = _random_vectors(tl, nbody, 9, np.random.default_rng(5 + nbody))
+    tame[:, 0:2 * nbody:2] += ox
+    tame[:, 1:2 * nbody:2] += oy
+    wild = tame[:4].copy()
+    sx, sy, sx2, _ = lay.i_sigma
+    wild[0, sx] = 0.3; wild[0, sy] = 0.35                        # needle core: outside the safe range
+    wild[1, 0] -= 400.0                                          # star far outside the stamp
+    wild[2, lay.i_amp(0)] = 3e13                                 # enormous amplitude
+    wild[3, sx2] = float("nan")                                  # nan shape
+    vecs = np.concatenate([tame, wild]).astype(np.float32).astype(np.float64)   # 13 vectors: odd
+    n = len(vecs)
+    model, chi2 = (t.cpu().numpy() for t in dom.model_chi2(vecs, want_model=True))
+    img64 = img.astype(np.float64)
+    w = orc.weight_map(img64, HEADER)
+    for i in range(n - 1):                                       # the last one is nan
+        m = orc.model_image(vecs[i], lay, size, size, origin=(ox, oy))
+        assert np.max(np.abs(model[i] - m) / np.abs(m)) < RTOL, i
+        assert chi2[i] == pytest.approx(orc.chi_squared_weighted(img64, m, w), rel=RTOL)
+    assert np.isnan(chi2[-1])
+    # alone
+    for i in range(n):
+        m1, c1 = (t.cpu().numpy() for t in dom.model_chi2(vecs[i:i + 1], want_model=True))
+        assert np.array_equal(c1, chi2[i:i + 1], equal_nan=True), i
+        assert np.array_equal(m1[0], model[i], equal_nan=True), i
+    # every ordered pair (a, b): a in the lower half warp, b in the upper
+    ia, ib = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    pairs = np.stack([vecs[ia.ravel()], vecs[ib.ravel()]], axis=1).reshape(-1, vecs.shape[1])
+    _, cp = dom.model_chi2(pairs)
+    cp = cp.cpu().numpy().reshape(n, n, 2)
+    assert np.array_equal(cp[..., 0], np.broadcast_to(chi2[:, None], (n, n)), equal_nan=True)
+    assert np.array_equal(cp[..., 1], np.broadcast_to(chi2[None, :], (n, n)), equal_nan=True)
+    # and the sampler (walkers in both halves, an odd number of them, tame and wild starting points):
+    # the state's chi-square is the stateless operator's on the state, bit for bit
+    init = vecs[:n - 1][[0, 9, 1, 10, 2, 11, 3]]                 # 7 walkers; 9-11 are wild
+    with gpu["sampler"].GibbsSampler(dom, init, seed=17) as s:
+        s.run(64)
+        st = s.state()[0].cpu().numpy()
+    _, c = dom.model_chi2(np.ascontiguousarray(st[:, :-1]))
+    assert np.array_equal(c.cpu().numpy(), st[:, -1])
+
+
 def test_batched_sampler_partitions(gpu):
     """The batched kernel deals walkers to CTAs, warps and lanes: ragged frames, frames without
     walkers, fewer walkers than SMs, more walkers of one frame than a CTA holds at once.  Whatever
