@@ -2,14 +2,14 @@
 """Experiment: model images and chi-squares of the stateless operator for fixed vectors, written
 to an .npz so builds of the library (LAPF_LIB) can be compared offline and against the oracle.
 
-    LAPF_LIB=build/exp/liblapf_split.so python tools/exp_k1dump.py out.npz
+    LAPF_LIB=build/exp/liblapf_split.so python tests/diag/exp_k1dump.py out.npz
 """
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from olpefit_b200 import frame, synth  # noqa: E402
 from oracle import lapf_oracle as orc  # noqa: E402  (experiment script: the oracle is the checker here)

@@ -2,11 +2,11 @@
 a failing build and say which trial vectors differ (by how much, which path, which lane parity)."""
 import os, sys, json
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 os.environ["LAPF_SELFTEST_DUMP"] = "/tmp/selftest.bin"
 import torch
 from olpefit_b200 import frame, sampler, _lib
-from oracle import lapf_oracle as orc   # diagnosis only
+from oracle import lapf_oracle as orc   # the checker (this script is test infrastructure: tests/diag)
 from olpefit_b200 import synth
 HEADER = {"itime": 1.0, "coadds": 1, "multisam": 1, "sampmode": 2}
 
