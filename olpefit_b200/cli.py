@@ -156,10 +156,14 @@ def run(kind, nbody, argv=None):
     team = args.team
     if team == 0:
         team = 16 if (total_walkers <= 220 * world and args.stamp >= 64) else (4 if total_walkers <= 1800 * world else 1)
-    # global walker g = frame * per_frame + w: walker w of epoch `frame` (the reference's rank w of that image)
+    # Global walker g = w * n_frames + frame: walker w of epoch `frame` (the reference's rank w of that image;
+    # one epoch: g = w).  Ranks own g = rank (mod world), so with the epochs a multiple of the ranks every rank
+    # owns WHOLE epochs (frame = rank mod world): its warps fill with walkers of one stamp (1,048 per
+    # epoch instead of 131 at a million walkers, 1,000 epochs, 8 GPUs: +26 % at 32 pixels), and the
+    # random streams -- keyed by g -- do not depend on the number of ranks.
     ids = np.array([id_base + i * id_stride for i in range(n_local)], dtype=np.int64)
     ids_or_0 = ids if n_local else np.zeros(1, dtype=np.int64)
-    frame_of = (ids_or_0 // per_frame).astype(np.int32)
+    frame_of = (ids_or_0 % n_frames).astype(np.int32)
     sam = smp.GibbsSampler(dom, params[frame_of], frame_of, seed=seed, burn_in=burn_in,
                            thin=args.thin, id_base=id_base, id_stride=id_stride, team_warps=team)
     st0, _, _ = sam.state()
@@ -173,8 +177,8 @@ def run(kind, nbody, argv=None):
         paths = [outdirs[f] + "step2a.csv" for f in frame_of[:n_local]]
         acc_paths = [outdirs[f] + "step2a_acceptance_rate" for f in frame_of[:n_local]]
     else:
-        paths = [outdirs[g // per_frame] + "%d_finalarray_mpi.csv" % (g % per_frame) for g in ids]
-        acc_paths = [outdirs[g // per_frame] + "%d_acceptance_rate.csv" % (g % per_frame) for g in ids]
+        paths = [outdirs[g % n_frames] + "%d_finalarray_mpi.csv" % (g // n_frames) for g in ids]
+        acc_paths = [outdirs[g % n_frames] + "%d_acceptance_rate.csv" % (g // n_frames) for g in ids]
 
     # separation / position angle of every recorded row, binned on the device (one centre per epoch,
     # the same on every rank: the starting point)
@@ -195,6 +199,7 @@ def run(kind, nbody, argv=None):
         packed = chains.PackedChainWriter(
             outdirs[0] + "chains_rank%d" % rank, max(n_local, 1), P + 1,
             {"walker_ids": ids.tolist(), "walkers_per_frame": per_frame, "frames": images, "seed": seed,
+             "id_layout": "walker_id = walker * n_frames + frame",
              "burn_in": burn_in, "thin": args.thin, "nbody": nbody, "origin": [int(v) for v in cuts[0]],
              "cuts": cuts.tolist(), "stamp": args.stamp},
             dtype="float32" if args.chain_dtype == "f32" else "float64",
