@@ -302,6 +302,11 @@ struct RunArgs {
     const int32_t* item_frame;   // [n_items]
     const int32_t* item_first;   // [n_items] offset into walker_of
     const int32_t* item_count;   // [n_items] walkers in the item (<= warps per CTA)
+    // batched kernel: an item may hold walkers of TWO frames, both resident in the pixel store (slots 0 and 1):
+    // the first item_count_a walkers belong to the frame of slot item_slot_a, the others to the other slot
+    const int32_t* item_frame2;  // [n_items] frame of slot 1 (-1: none); item_frame is the frame of slot 0
+    const int32_t* item_count_a; // [n_items]
+    const int32_t* item_slot_a;  // [n_items]
     const int32_t* walker_of;    // local walker indices grouped by frame
     const int32_t* cta_item;     // [grid + 1] first item of every CTA (batched kernel only)
     double* state;               // [W][P+1]  parameters, chi-square
@@ -574,9 +579,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
 // and at most one written per update).  The arithmetic per walker is the one of run_walker: chains
 // are bit-identical between the two forms.
 // ---------------------------------------------------------------------------------------------
+// `frame`, `slot`: the lane's walker's frame and the pixel-store slot that holds it; `la`: lanes [0, la) of
+// this warp use one slot, [la, nl) the other (la = nl: one frame); `slot_cols`: TMEM columns per slot.
 template <int NB, int NX, int NY, int LW, int TM, int WPP>
 __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, const float* sw, float* rt, float* img,
-                                          int wl, int nl, int frame, int lane, uint32_t tmem) {
+                                          int wl, int nl, int la, int frame, int slot, int lane, uint32_t tmem,
+                                          uint32_t slot_cols) {
     using L = Layout<NB>;
     using I = CoefImg<NB, Geo<NX>::PANELS>;
     constexpr int P = L::P;
@@ -621,7 +629,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
             set_fast_serial<NB, NX, NY>(cf);
             if (a.plain) cf.fast = false;
             if (NX >= 64 && a.cull) set_cull_serial<NB, NX, NY>(cf); else no_cull<NB, NX, NY>(cf);
-            store_coef<NB, Geo<NX>::PANELS>(img + lane * I::STRIDE, cf);
+            store_coef<NB, Geo<NX>::PANELS>(img + lane * I::STRIDE, cf, slot);
         }
         __syncwarp();
 
@@ -631,24 +639,34 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
 #pragma unroll 1
             for (int i = 0; i < nl; ++i) {
                 Coef<NB> cf;
-                load_coef<NB, Geo<NX>::PANELS>(cf, img + i * I::STRIDE);
+                int sl = 0;
+                load_coef<NB, Geo<NX>::PANELS>(cf, img + i * I::STRIDE, &sl);
                 unsigned e_upd = 0;
-                const double c = warp_chi2<NB, NX, NY, false, true, 1, TM>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd, tmem);   // :314-316
+                const double c = warp_chi2<NB, NX, NY, false, true, 1, TM>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd,
+                                                                           TM == 1 ? tmem + (uint32_t)sl * slot_cols : tmem);   // :314-316
                 if (lane == i) { chi_t = c; n_exps += e_upd; }
             }
         } else {
-            // two walkers per pass: lanes 0-15 evaluate walker i, lanes 16-31 walker i + 1 (or i again, discarded)
+            // two walkers per pass: lanes 0-15 evaluate walker i, lanes 16-31 walker i + 1 (or i again, discarded);
+            // both of the same pixel-store slot (the TMEM address of a load is the warp's): walkers [0, la), then [la, nl)
 #pragma unroll 1
-            for (int i = 0; i < nl; i += 2) {
-                const int mine_i = min(i + (lane >> 4), nl - 1);
-                Coef<NB> cf;
-                load_coef<NB, 1>(cf, img + mine_i * I::STRIDE);
-                unsigned e_upd = 0;
-                const double c = warp_chi2_pair<NB, NX, NY, false, true, TM>(cf, rt, sd, sw, nullptr, lane, &e_upd, tmem);   // :314-316
-                const double c0 = shfl_f64(c, 0), c1 = shfl_f64(c, 16);
-                const unsigned e0 = __shfl_sync(kFull, e_upd, 0), e1 = __shfl_sync(kFull, e_upd, 16);
-                if (lane == i) { chi_t = c0; n_exps += e0; }
-                if (lane == i + 1) { chi_t = c1; n_exps += e1; }
+            for (int seg = 0; seg < 2; ++seg) {
+                const int i0 = seg ? la : 0, i1 = seg ? nl : la;
+#pragma unroll 1
+                for (int i = i0; i < i1; i += 2) {
+                    const int mine_i = min(i + (lane >> 4), i1 - 1);
+                    Coef<NB> cf;
+                    int sl = 0;
+                    load_coef<NB, 1>(cf, img + mine_i * I::STRIDE, &sl);
+                    sl = __shfl_sync(kFull, sl, 0);
+                    unsigned e_upd = 0;
+                    const double c = warp_chi2_pair<NB, NX, NY, false, true, TM>(cf, rt, sd, sw, nullptr, lane, &e_upd,
+                                                                                 tmem + (uint32_t)sl * slot_cols);   // :314-316
+                    const double c0 = shfl_f64(c, 0), c1 = shfl_f64(c, 16);
+                    const unsigned e0 = __shfl_sync(kFull, e_upd, 0), e1 = __shfl_sync(kFull, e_upd, 16);
+                    if (lane == i) { chi_t = c0; n_exps += e0; }
+                    if (lane == i + 1 && i + 1 < i1) { chi_t = c1; n_exps += e1; }
+                }
             }
         }
         __syncwarp();   // every pass has read its image before the next round overwrites it
@@ -712,7 +730,11 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
     // stamps of up to 64 x 64 pixels also live in the TMEM pixel store (see tmem_fill_stamp)
     // (128 x 128: the weight plane only, the data plane is read from shared memory)
     constexpr int TM = (Geo<NX>::PANELS == 1 && Rows<NY, 1>::HALVES == 1) ? 1 : 2;
-    constexpr uint32_t TM_COLS = TM == 1 ? 16 * (NY / Geo<NX, WPP>::RG) : 512;
+    // TM == 1: the pixel store has TWO slots, so that an item can hold walkers of two frames (the shared-memory
+    // planes are then only where a stamp is staged and converted; both loops read the pixel store)
+    constexpr uint32_t SLOT_COLS = TM == 1 ? 16 * (NY / Geo<NX, WPP>::RG) : 512;
+    constexpr int SLOTS = TM == 1 ? 2 : 1;
+    constexpr uint32_t TM_COLS = SLOTS * SLOT_COLS;
     static_assert(TM_COLS >= 32 && TM_COLS <= 512 && (TM_COLS & (TM_COLS - 1)) == 0, "TMEM allocations are powers of two");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
@@ -731,12 +753,15 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
     const uint32_t tmem_base = TM ? tmem_slot : 0u;
 
     const int i0 = a.cta_item[blockIdx.x], i1 = a.cta_item[blockIdx.x + 1];
-    int cur_frame = -1;
+    int cur_frame[2] = {-1, -1};
     uint32_t phase = 0;
     for (int it = i0; it < i1; ++it) {
-        const int f = a.item_frame[it];
-        if (f != cur_frame) {
-            __syncthreads();   // every warp has finished reading the previous stamp
+        const int fr[2] = {a.item_frame[it], a.item_frame2[it]};
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) {
+            const int f = fr[sl];
+            if (f < 0 || f == cur_frame[sl]) continue;          // (uniform over the CTA)
+            __syncthreads();   // every warp has finished with the previous stamp (and with the staging planes)
             if (threadIdx.x == 0) {
                 constexpr uint32_t kBytes = NX * NY * sizeof(float);
                 fence_proxy_async();
@@ -746,25 +771,30 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
             }
             mbar_wait(&bar, phase);
             phase ^= 1u;
-            cur_frame = f;
+            cur_frame[sl] = f;
             prep_stamp(sd, sw, NX * NY);            // (d, w) -> (d*sqrt(w), -sqrt(w)), once per staged frame
             __syncthreads();
             {
-                if constexpr (TM == 1) { if (warp < 4) tmem_fill_stamp<NX, NY, WPP>(tmem_base, sd, sw, warp, lane); }
+                if constexpr (TM == 1) { if (warp < 4) tmem_fill_stamp<NX, NY, WPP>(tmem_base + (uint32_t)sl * SLOT_COLS, sd, sw, warp, lane); }
                 else { if (warp < 4) tmem_fill_weights<NX, NY>(tmem_base, sw, warp, lane); }
                 tmem_fence_before_sync();
                 __syncthreads();
                 tmem_fence_after_sync();
             }
         }
-        // walker j of the item goes to warp j % NW, lane j / NW: the warps' loads differ by at most one
-        const int n = a.item_count[it];
+        // walker j of the item goes to warp j % NW, lane j / NW: the warps' loads differ by at most one.  The first
+        // na walkers are of the frame in slot sa, the others of the frame in the other slot.
+        const int n = a.item_count[it], na = a.item_count_a[it], sa = a.item_slot_a[it];
         const int nl = n > warp ? (n - warp + NW - 1) / NW : 0;
+        const int la = na > warp ? min((na - warp + NW - 1) / NW, nl) : 0;
         const int j = warp + NW * lane;
+        const int slot = (lane < la) ? sa : 1 - sa;
+        const int fsel = slot ? fr[1] : fr[0];
         if (nl > 0)
             run_batch<NB, NX, NY, LW, TM, WPP>(a, sd, sw, rt + warp * TAB, img + warp * (LW * I::STRIDE),
-                                          (lane < nl) ? a.walker_of[a.item_first[it] + j] : -1, nl, f, lane,
-                                          tmem_base + ((uint32_t)(32 * (warp & 3)) << 16));
+                                          (lane < nl) ? a.walker_of[a.item_first[it] + j] : -1, nl, la,
+                                          fsel < 0 ? fr[0] : fsel, slot, lane,
+                                          tmem_base + ((uint32_t)(32 * (warp & 3)) << 16), SLOT_COLS);
     }
     if (TM) {
         tmem_fence_before_sync();
@@ -1128,6 +1158,9 @@ struct lapf_sampler {
     int32_t* item_frame = nullptr;
     int32_t* item_first = nullptr;
     int32_t* item_count = nullptr;
+    int32_t* item_frame2 = nullptr;   // batched kernel: second resident frame of an item (see RunArgs)
+    int32_t* item_count_a = nullptr;
+    int32_t* item_slot_a = nullptr;
     int32_t* cta_item = nullptr;   // batched kernel: first item of every CTA
     int32_t* frame_of = nullptr;   // [W] the caller's frame index per walker (a copy: reset and the self-test need it)
     // chain rows leave as double values or as float differences from the starting point
@@ -1388,6 +1421,7 @@ static void free_sampler(lapf_sampler* s) {
     cudaFree(s->state); cudaFree(s->shift); cudaFree(s->moments); cudaFree(s->tries); cudaFree(s->accepts); cudaFree(s->exps);
     cudaFree(s->walker_of); cudaFree(s->frame_start); cudaFree(s->item_frame); cudaFree(s->item_first);
     cudaFree(s->item_count); cudaFree(s->cta_item); cudaFree(s->frame_of);
+    cudaFree(s->item_frame2); cudaFree(s->item_count_a); cudaFree(s->item_slot_a);
     cudaFree(s->sk_hist); cudaFree(s->sk_center); cudaFree(s->sk_mom);
     delete s;
 }
@@ -1453,24 +1487,46 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     for (int f = 0; f < F; ++f) start[f + 1] += start[f];
     std::vector<int32_t> order((size_t)W), fill(start.begin(), start.end() - 1);
     for (int64_t w = 0; w < W; ++w) order[fill[fo[w]]++] = (int32_t)w;
-    std::vector<int32_t> it_frame, it_first, it_count, cta_item;
+    std::vector<int32_t> it_frame, it_first, it_count, cta_item, it_frame2, it_count_a, it_slot_a;
     if (s->team == 1) {
-        // batched kernel: CTA b owns the contiguous share [b W / G, (b+1) W / G) of the frame-sorted
-        // walkers, cut into items at frame boundaries and at the CTA's capacity
+        // Batched kernel: CTA b owns the contiguous share [b W / G, (b+1) W / G) of the frame-sorted walkers, cut
+        // into items of at most `chunk` walkers.  Up to 64 x 64 pixels the pixel store holds two stamps, and an
+        // item may then run across ONE frame boundary: its first part is evaluated on one slot, the rest on the
+        // other.  (Otherwise a share of 443 walkers over frames of 655 is two items of ~220, i.e. ~14 of a
+        // warp's 32 lanes busy in the one-walker-per-lane section of every round.)  A frame stays in the slot
+        // it was staged into while consecutive items of the CTA need it.
         const int64_t G = std::min<int64_t>(s->grid, W);
+        const bool two = pb.nx <= 64;
         s->launch_grid = (int)G;
         int f = 0;
         for (int64_t b = 0; b < G; ++b) {
             cta_item.push_back((int32_t)it_frame.size());
             int64_t lo = (W * b) / G;
             const int64_t hi = (W * (b + 1)) / G;
+            int slot_frame[2] = {-1, -1};
             while (lo < hi) {
                 while (start[f + 1] <= lo) ++f;
-                const int64_t n = std::min<int64_t>(std::min<int64_t>(hi, start[f + 1]) - lo, s->chunk);
-                it_frame.push_back(f);
+                const int64_t n = std::min<int64_t>(hi - lo, s->chunk);                 // walkers of this item
+                const int64_t na = std::min<int64_t>(n, start[f + 1] - lo);              // ... of frame f
+                int f2 = -1;
+                int64_t nb = 0;
+                if (two && na < n) {                                                     // the rest: the next frame with walkers
+                    f2 = f + 1;
+                    while (start[f2 + 1] <= lo + na) ++f2;
+                    nb = std::min<int64_t>(n - na, start[f2 + 1] - (lo + na));
+                }
+                // slot of frame f: where it already is, else the slot that does not hold f2
+                int sa = (slot_frame[1] == f) ? 1 : (slot_frame[0] == f) ? 0 : (f2 >= 0 && slot_frame[0] == f2) ? 1 : 0;
+                if (!two) sa = 0;
+                slot_frame[sa] = f;
+                if (f2 >= 0) slot_frame[1 - sa] = f2;
+                it_frame.push_back(slot_frame[0]);
+                it_frame2.push_back(two ? slot_frame[1] : -1);
                 it_first.push_back((int32_t)lo);
-                it_count.push_back((int32_t)n);
-                lo += n;
+                it_count.push_back((int32_t)(na + nb));
+                it_count_a.push_back((int32_t)na);
+                it_slot_a.push_back(sa);
+                lo += na + nb;
             }
         }
         cta_item.push_back((int32_t)it_frame.size());
@@ -1497,6 +1553,14 @@ int lapf_sampler_create(const lapf_config* cfg, lapf_sampler** out, void* stream
     CUS(cudaMalloc((void**)&s->item_frame, sizeof(int32_t) * s->n_items));
     CUS(cudaMalloc((void**)&s->item_first, sizeof(int32_t) * s->n_items));
     CUS(cudaMalloc((void**)&s->item_count, sizeof(int32_t) * s->n_items));
+    if (s->team == 1) {
+        CUS(cudaMalloc((void**)&s->item_frame2, sizeof(int32_t) * s->n_items));
+        CUS(cudaMalloc((void**)&s->item_count_a, sizeof(int32_t) * s->n_items));
+        CUS(cudaMalloc((void**)&s->item_slot_a, sizeof(int32_t) * s->n_items));
+        CUS(cudaMemcpyAsync(s->item_frame2, it_frame2.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
+        CUS(cudaMemcpyAsync(s->item_count_a, it_count_a.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
+        CUS(cudaMemcpyAsync(s->item_slot_a, it_slot_a.data(), sizeof(int32_t) * s->n_items, cudaMemcpyHostToDevice, st));
+    }
     CUS(cudaMalloc((void**)&s->cta_item, sizeof(int32_t) * cta_item.size()));
     CUS(cudaMalloc((void**)&s->frame_of, sizeof(int32_t) * W));
     CUS(cudaMemcpyAsync(s->frame_of, fo.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, st));
@@ -1644,6 +1708,7 @@ static void fill_run_args(const lapf_sampler* s, RunArgs& a, int64_t n_updates, 
     const lapf_problem& pb = s->cfg.problem;
     a.data = pb.data; a.weight = pb.weight; a.origin = pb.origin; a.outside = pb.outside;
     a.item_frame = s->item_frame; a.item_first = s->item_first; a.item_count = s->item_count;
+    a.item_frame2 = s->item_frame2; a.item_count_a = s->item_count_a; a.item_slot_a = s->item_slot_a;
     a.walker_of = s->walker_of; a.cta_item = s->cta_item;
     a.state = s->state; a.shift = s->shift; a.moments = s->moments;
     a.tries = s->tries; a.accepts = s->accepts; a.exps = s->exps;

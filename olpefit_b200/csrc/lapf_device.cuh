@@ -262,13 +262,14 @@ __device__ __forceinline__ void load_shape(Coef<NB>& cf, int which, const float*
 template <int NB, int PANELS>
 struct CoefImg {
     static constexpr int K = 2 * NB;
-    static constexpr int WORDS = 3 * K + 7 + 4 * PANELS + 2;   // x0 y0 amp | sa sb sc floor | segments | nexp fast
+    static constexpr int WORDS = 3 * K + 7 + 4 * PANELS + 3;   // x0 y0 amp | sa sb sc floor | segments | nexp fast slot
     static constexpr int V4 = ((WORDS + 3) / 4) | 1;
     static constexpr int STRIDE = 4 * V4;             // floats per walker
 };
 
+// `slot`: which of the resident stamps (TMEM pixel-store slots of the batched sampler) the vector is evaluated on
 template <int NB, int PANELS>
-__device__ __forceinline__ void store_coef(float* __restrict__ dst, const Coef<NB>& cf) {
+__device__ __forceinline__ void store_coef(float* __restrict__ dst, const Coef<NB>& cf, int slot = 0) {
     constexpr int K = 2 * NB;
     using I = CoefImg<NB, PANELS>;
     float v[I::STRIDE];
@@ -285,13 +286,14 @@ __device__ __forceinline__ void store_coef(float* __restrict__ dst, const Coef<N
         for (int q = 0; q < 4; ++q) v[3 * K + 7 + 4 * p + q] = __int_as_float(cf.seg[p][q]);
     v[3 * K + 7 + 4 * PANELS] = __uint_as_float(cf.nexp);
     v[3 * K + 8 + 4 * PANELS] = __int_as_float(cf.fast ? 1 : 0);
+    v[3 * K + 9 + 4 * PANELS] = __int_as_float(slot);
 #pragma unroll
     for (int q = 0; q < I::V4; ++q)
         reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 template <int NB, int PANELS>
-__device__ __forceinline__ void load_coef(Coef<NB>& cf, const float* __restrict__ src) {
+__device__ __forceinline__ void load_coef(Coef<NB>& cf, const float* __restrict__ src, int* slot = nullptr) {
     constexpr int K = 2 * NB;
     using I = CoefImg<NB, PANELS>;
     float v[I::STRIDE];
@@ -311,6 +313,7 @@ __device__ __forceinline__ void load_coef(Coef<NB>& cf, const float* __restrict_
         for (int q = 0; q < 4; ++q) cf.seg[p][q] = __float_as_int(v[3 * K + 7 + 4 * p + q]);
     cf.nexp = __float_as_uint(v[3 * K + 7 + 4 * PANELS]);
     cf.fast = __float_as_int(v[3 * K + 8 + 4 * PANELS]) != 0;
+    if (slot) *slot = __float_as_int(v[3 * K + 9 + 4 * PANELS]);
 }
 
 // Coefficients of a parameter vector given in FP64 frame coordinates, by ONE thread: the same
@@ -700,21 +703,35 @@ __device__ __forceinline__ void finish_step(const float2 (&m)[4], const float4& 
 // coefficients as broadcast operands) -- 3 FFMA2 + 2 MUFU.EX2 per pixel PAIR and component:
 // SFU-bound.  Kept for parameter vectors set_fast turns away; it takes no table (the row terms are
 // worked out per row on the spot).
-template <int NB, int NX, int NY, bool STORE, bool PREP, int WPP = 1>
+template <int NB, int NX, int NY, bool STORE, bool PREP, int WPP = 1, int TM = 0>
 __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)[2 * NB][2], float2& s0, float2& s1,
                                           int& i, int i1, StepPtrs& sp, bool keep = true) {
     using G = Geo<NX, WPP>;
     constexpr int K = 2 * NB;
+    static_assert(TM == 0 || TM == 1, "the plain loop reads both planes from one place");
     const float* dp = sp.dp;
     const float* wp = sp.wp;
     float* mp = sp.mp;
     float row = sp.row;
+    uint32_t tm = sp.tm;
 #pragma unroll 1
     for (; i < i1; ++i) {
-        const float4 d0 = *reinterpret_cast<const float4*>(dp);
-        const float4 d1 = *reinterpret_cast<const float4*>(dp + NX);
-        const float4 w0 = *reinterpret_cast<const float4*>(wp);
-        const float4 w1 = *reinterpret_cast<const float4*>(wp + NX);
+        float4 d0, d1, w0, w1;
+        if (TM == 1) {      // the step's 16 values from the TMEM pixel store (same layout as row_steps_fast)
+            uint32_t tv[16];
+            tmem_ld16_issue(tm, tv);
+            tmem_ld16_wait(tv);
+            d0 = make_float4(__uint_as_float(tv[0]), __uint_as_float(tv[1]), __uint_as_float(tv[2]), __uint_as_float(tv[3]));
+            d1 = make_float4(__uint_as_float(tv[4]), __uint_as_float(tv[5]), __uint_as_float(tv[6]), __uint_as_float(tv[7]));
+            w0 = make_float4(__uint_as_float(tv[8]), __uint_as_float(tv[9]), __uint_as_float(tv[10]), __uint_as_float(tv[11]));
+            w1 = make_float4(__uint_as_float(tv[12]), __uint_as_float(tv[13]), __uint_as_float(tv[14]), __uint_as_float(tv[15]));
+            tm += 16;
+        } else {
+            d0 = *reinterpret_cast<const float4*>(dp);
+            d1 = *reinterpret_cast<const float4*>(dp + NX);
+            w0 = *reinterpret_cast<const float4*>(wp);
+            w1 = *reinterpret_cast<const float4*>(wp + NX);
+        }
         float2 m[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) m[j] = make_float2(cf.floor, cf.floor);
@@ -741,7 +758,7 @@ __device__ __forceinline__ void row_steps(const Coef<NB>& cf, const float2 (&xd)
         wp += G::RG * NX;
         row += (float)G::RG;
     }
-    sp.dp = dp; sp.wp = wp; sp.mp = mp; sp.row = row;
+    sp.dp = dp; sp.wp = wp; sp.mp = mp; sp.row = row; sp.tm = tm;
 }
 
 // ---- factorised loop -------------------------------------------------------------------------
@@ -1053,10 +1070,10 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
                 for (int mth = 0; mth < STEPS / TEAM; ++mth) {
                     const int st = mth * TEAM + tw;
                     const int so = st * G::RG * NX;
-                    StepPtrs sp{nullptr, d + off0 + so, w + off0 + so, STORE ? model_out + off0 + so : nullptr, 0u,
-                                (float)(half * TR + st * G::RG + 2 * b)};
+                    StepPtrs sp{nullptr, d + off0 + so, w + off0 + so, STORE ? model_out + off0 + so : nullptr,
+                                TM == 1 ? tmem + (uint32_t)(st * 16) : 0u, (float)(half * TR + st * G::RG + 2 * b)};
                     int i = 0;
-                    row_steps<NB, NX, NY, STORE, PREP>(cf, xd, s0, s1, i, 1, sp);
+                    row_steps<NB, NX, NY, STORE, PREP, 1, (TM == 1 ? 1 : 0)>(cf, xd, s0, s1, i, 1, sp);
                 }
             }
             // FP32 partial sums of one panel (at most 16 steps x 8 pixels over 4 accumulators) -> FP64
@@ -1114,10 +1131,10 @@ __device__ __forceinline__ double warp_chi2_pair(const Coef<NB>& cf, float* __re
 #pragma unroll 1
         for (int st = 0; st < STEPS; ++st) {
             const int so = st * G::RG * NX;
-            StepPtrs sp{nullptr, d + off0 + so, w + off0 + so, STORE ? model_out + off0 + so : nullptr, 0u,
-                        (float)(st * G::RG + 2 * b)};
+            StepPtrs sp{nullptr, d + off0 + so, w + off0 + so, STORE ? model_out + off0 + so : nullptr,
+                        TM == 1 ? tmem + (uint32_t)(st * 16) : 0u, (float)(st * G::RG + 2 * b)};
             int i = 0;
-            row_steps<NB, NX, NY, STORE, PREP, 2>(cf, xd, p0, p1, i, 1, sp, !cf.fast);
+            row_steps<NB, NX, NY, STORE, PREP, 2, (TM == 1 ? 1 : 0)>(cf, xd, p0, p1, i, 1, sp, !cf.fast);
         }
         if (!cf.fast) { s0 = p0; s1 = p1; }
     }

@@ -32,7 +32,7 @@ def test_native_instructions_are_present(kernels):
     for name, ins in batch.items():
         ops = [x.op for x in ins]
         assert any(o.startswith("LDTM") for o in ops) and any(o.startswith("STTM") for o in ops), name
-        assert sum(o == "UBLKCP.S.G" for o in ops) == 2, name
+        assert sum(o == "UBLKCP.S.G" for o in ops) in (2, 4), name      # two planes per stamp slot (two slots up to 64 pixels)
         assert sum(o == "FFMA2" for o in ops) > 100 and "MUFU.EX2" in ops, name
         assert not any("MMA" in o for o in ops), name
     prep = [v for k, v in fns.items() if "frame_prep_tma_kernel" in k]
