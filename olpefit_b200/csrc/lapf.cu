@@ -579,18 +579,23 @@ __global__ void __launch_bounds__(NW * 32, MINB) gibbs_kernel(const __grid_const
 // and at most one written per update).  The arithmetic per walker is the one of run_walker: chains
 // are bit-identical between the two forms.
 // ---------------------------------------------------------------------------------------------
-// `frame`, `slot`: the lane's walker's frame and the pixel-store slot that holds it; `la`: lanes [0, la) of
-// this warp use one slot, [la, nl) the other (la = nl: one frame); `slot_cols`: TMEM columns per slot.
+// `frame0`, `frame1`: the frames in the two pixel-store slots (frame1 < 0: none; both uniform over the CTA);
+// `slot`: the slot of the lane's walker; `la`: lanes [0, la) of this warp use one slot, [la, nl) the other
+// (la = nl: one frame); `slot_cols`: TMEM columns per slot.  Everything per frame is kept uniform and picked
+// by `slot` where it is used: a per-lane frame held the origins in vector registers through the passes and
+// cost 2 % at 128 pixels.
 template <int NB, int NX, int NY, int LW, int TM, int WPP>
 __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, const float* sw, float* rt, float* img,
-                                          int wl, int nl, int la, int frame, int slot, int lane, uint32_t tmem,
-                                          uint32_t slot_cols) {
+                                          int wl, int nl, int la, int frame0, int frame1, int slot, int lane,
+                                          uint32_t tmem, uint32_t slot_cols) {
     using L = Layout<NB>;
     using I = CoefImg<NB, Geo<NX>::PANELS>;
     constexpr int P = L::P;
     const bool mine = wl >= 0;
     const uint64_t gid = (uint64_t)(a.id_base + (int64_t)wl * a.id_stride);
-    const double oxd = (double)a.origin[2 * frame], oyd = (double)a.origin[2 * frame + 1];
+    const bool two = TM == 1 && frame1 >= 0;
+    const int ox0 = a.origin[2 * frame0], oy0 = a.origin[2 * frame0 + 1];
+    const int ox1 = two ? a.origin[2 * frame1] : ox0, oy1 = two ? a.origin[2 * frame1 + 1] : oy0;
     double* st = a.state + (size_t)(mine ? wl : 0) * (P + 1);
     double chi_c = mine ? st[P] : 0.0;
 
@@ -606,6 +611,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
         double nv = 0.0, lnu = 0.0;
         if (mine) {
             const Draw dr = make_draw(a.seed, gid, (uint64_t)(a.t0 + u), P);   // apf_step2.py:302, :64/:68, :143
+            const double oxd = (double)((two && slot) ? ox1 : ox0), oyd = (double)((two && slot) ? oy1 : oy0);
             k = dr.k;
             lnu = dr.lnu;
             const double wz = __dmul_rn(a.widths[k], dr.z);
@@ -676,7 +682,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
             if (a.outside) {
                 double fl = st[a.floor_index];
                 if (k == a.floor_index) fl = nv;
-                chi_t += outside_chi2(a.outside, frame, fl);
+                chi_t += outside_chi2(a.outside, (two && slot) ? frame1 : frame0, fl);
             }
             // accept iff u < exp(-(chi_t - chi_c)/2) (apf_step2.py:139-148); false on nan
             const bool acc = lnu < -0.5 * (chi_t - chi_c);
@@ -705,7 +711,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
                     double xy[2 * NB];
 #pragma unroll
                     for (int j = 0; j < 2 * NB; ++j) xy[j] = st[j];
-                    record_sketch<NB>(a, wl, frame, xy);
+                    record_sketch<NB>(a, wl, (two && slot) ? frame1 : frame0, xy);
                 }
                 if (a.probe) {                                            // lapf_sampler_selftest
                     double* pb = a.probe + ((size_t)row * a.n_walkers + wl) * 3;
@@ -789,11 +795,10 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
         const int la = na > warp ? min((na - warp + NW - 1) / NW, nl) : 0;
         const int j = warp + NW * lane;
         const int slot = (lane < la) ? sa : 1 - sa;
-        const int fsel = slot ? fr[1] : fr[0];
         if (nl > 0)
             run_batch<NB, NX, NY, LW, TM, WPP>(a, sd, sw, rt + warp * TAB, img + warp * (LW * I::STRIDE),
                                           (lane < nl) ? a.walker_of[a.item_first[it] + j] : -1, nl, la,
-                                          fsel < 0 ? fr[0] : fsel, slot, lane,
+                                          fr[0], SLOTS > 1 ? fr[1] : -1, slot, lane,
                                           tmem_base + ((uint32_t)(32 * (warp & 3)) << 16), SLOT_COLS);
     }
     if (TM) {
