@@ -765,12 +765,15 @@ def test_two_vectors_per_pass_are_independent_of_their_partner(gpu, nbody):
     assert np.array_equal(c.cpu().numpy(), st[:, -1])
 
 
-def test_batched_sampler_partitions(gpu):
+@pytest.mark.parametrize("size", [32, 64])
+def test_batched_sampler_partitions(gpu, size):
     """The batched kernel deals walkers to CTAs, warps and lanes: ragged frames, frames without
-    walkers, fewer walkers than SMs, more walkers of one frame than a CTA holds at once.  Whatever
-    the shape, a walker's chain is the chain it has when it runs alone under the same id."""
+    walkers, fewer walkers than SMs, more walkers of one frame than a CTA holds at once, items
+    that run across a frame boundary with both stamps resident (two pixel-store slots; on 32-pixel
+    stamps also two walkers per pass).  Whatever the shape, a walker's chain is the chain it has
+    when it runs alone under the same id."""
     torch = gpu["torch"]
-    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 32, n_frames=7)
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, size, n_frames=7)
     rng = np.random.default_rng(8)
 
     def solo(frame, gid, start, n_upd, seed):
