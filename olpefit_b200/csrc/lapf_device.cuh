@@ -401,7 +401,9 @@ template <int NB, int NX, int NY, int TEAM = 1, int WPP = 1>
 struct Scratch {
     // block table of one vector (two vectors per pass: 8 floats apart in the banks, so the four blocks
     // a warp step reads -- 2 block rows x 2 vectors -- are one conflict-free wavefront)
-    static constexpr int TAB1 = Rows<NY, TEAM>::NBLK * Tab<NB>::RS + (WPP > 1 ? 8 : 0);
+    // (a team member's table: its share of the blocks of ONE panel over the whole height, see team_chi2)
+    static constexpr int TEAM_NBLK = NY * Geo<NX>::PANELS / (2 * TEAM);
+    static constexpr int TAB1 = (TEAM > 1 ? TEAM_NBLK : Rows<NY, TEAM>::NBLK) * Tab<NB>::RS + (WPP > 1 ? 8 : 0);
     static constexpr int TAB = WPP * TAB1;
     static constexpr int CT = 2 * NB * 2 * Geo<NX>::GPR * 4;      // column table of one panel and vector
     static constexpr int FLOATS = TAB + WPP * CT;                  // one warp on its own (TEAM = 1)
@@ -1081,6 +1083,62 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
         }
     }
     return warp_sum_f64(acc);
+}
+
+// TEAM > 1: this warp's share of chi-square of one parameter vector (the caller adds the TEAM partials
+// in a fixed order).  Warp tw works on ONE column panel (tw % PANELS) and on every (TEAM / PANELS)-th
+// warp step of it over the whole height of the stamp: one block table (its own steps only), one read
+// of the lane constants from the team's column table (team_consts), one run of MY steps.  (Round 1
+// gave a member every TEAM-th step of every panel and table half: on a 128-pixel stamp with 16 warps
+// that was four single-step loops, each with its own table build or constant read.)
+template <int NB, int NX, int NY, int TEAM>
+__device__ __forceinline__ double team_chi2(const Coef<NB>& cf, float* __restrict__ rt, const float* __restrict__ d,
+                                            const float* __restrict__ w, int lane, int tw, unsigned* exps,
+                                            const float* __restrict__ team_ct) {
+    using G = Geo<NX>;
+    using T = Tab<NB>;
+    constexpr int K = 2 * NB;
+    constexpr int RGROUPS = TEAM / G::PANELS;      // warps that share a panel
+    constexpr int TSTEPS = NY / G::RG;             // warp steps of a panel
+    constexpr int MY = TSTEPS / RGROUPS;           // ... of this warp
+    static_assert(TEAM > 1 && TEAM % G::PANELS == 0 && RGROUPS > 1 && TSTEPS % RGROUPS == 0, "unsupported team size");
+    static_assert(MY * G::BPS == Scratch<NB, NX, NY, TEAM>::TEAM_NBLK, "table size");
+    const int pan = tw % G::PANELS, rgp = tw / G::PANELS;
+    const int a = lane % G::GPR, b = lane / G::GPR;
+    const int off0 = (2 * b) * NX + pan * G::PW + 4 * a;   // the lane's block of warp step 0
+    if (exps) *exps += cf.nexp;
+    float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+    if (cf.fast) {
+        // blocks jb of the table: warp step (jb / BPS) * RGROUPS + rgp, block jb % BPS
+        build_row_table<NB, NX, NY, RGROUPS>(rt, cf, lane, 0, rgp);
+        LaneK<NB> lk;
+        read_consts<NB, NX>(lk, team_ct + pan * Scratch<NB, NX, NY, TEAM>::CT, cf, lane, pan);   // team_consts wrote it
+#pragma unroll(MY < 4 ? MY : 2)
+        for (int m = 0; m < MY; ++m) {
+            const int so = (m * RGROUPS + rgp) * G::RG * NX;
+            StepPtrs sp{rt + (m * G::BPS + b) * T::RS, d + off0 + so, w + off0 + so, nullptr, 0u, 0.f};
+            int i = 0;
+            row_steps_fast<NB, NX, NY, false, true, 2>(cf, lk, s0, s1, i, 1, sp);
+        }
+    } else {
+        float2 xd[K][2];   // column offsets of the lane's pixel pairs (0,1) and (2,3)
+        const float fa = (float)(pan * G::PW + 4 * a);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float2 nx0 = make_float2(-cf.x0[k], -cf.x0[k]);
+            xd[k][0] = __fadd2_rn(make_float2(fa, fa + 1.f), nx0);
+            xd[k][1] = __fadd2_rn(make_float2(fa + 2.f, fa + 3.f), nx0);
+        }
+#pragma unroll 1
+        for (int m = 0; m < MY; ++m) {
+            const int st = m * RGROUPS + rgp;
+            const int so = st * G::RG * NX;
+            StepPtrs sp{nullptr, d + off0 + so, w + off0 + so, nullptr, 0u, (float)(st * G::RG + 2 * b)};
+            int i = 0;
+            row_steps<NB, NX, NY, false, true>(cf, xd, s0, s1, i, 1, sp);
+        }
+    }
+    return warp_sum_f64((double)((s0.x + s0.y) + (s1.x + s1.y)));
 }
 
 // Two parameter vectors per pass on a 32-pixel stamp (Geo<NX, 2>): every lane holds the coefficients
