@@ -459,7 +459,7 @@ __device__ __forceinline__ void run_walker(const RunArgs& a, const float* sd, co
         unsigned e_upd = 0;
         double chi_t;                                                                                 // :314-316
         if constexpr (TEAM > 1) chi_t = team_chi2<NB, NX, NY, TEAM>(cf, rt, sd, sw, lane, tw, &e_upd, team_ct);
-        else chi_t = warp_chi2<NB, NX, NY, false, true, 1>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd, 0u, nullptr);
+        else chi_t = warp_chi2<NB, NX, NY, false, true, 1>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd, 0u);
         n_exps += e_upd;
         if (TEAM > 1) {
             double* slot_p = team_part + (u & 1) * TEAM;       // double-buffered: one barrier per update

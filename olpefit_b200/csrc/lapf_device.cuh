@@ -985,16 +985,16 @@ __device__ __forceinline__ void row_steps_fast(const Coef<NB>& cf, const LaneK<N
     sp.rp = rp; sp.dp = dp; sp.wp = wp; sp.mp = mp; sp.tm = tm;
 }
 
-// chi-square of one parameter vector over the stamp by ONE warp (TEAM = 1), or this warp's share
-// of it (TEAM > 1: warp `tw` takes every TEAM-th warp step; the caller adds the partials in a fixed
-// order).  Builds the block and column tables in `scratch` (Scratch<NB, NX, NY, TEAM>::FLOATS
+// chi-square of one parameter vector over the stamp by ONE warp (a team member's share: team_chi2).
+// Builds the block and column tables in `scratch` (Scratch<NB, NX, NY>::FLOATS
 // floats of this warp's own shared memory) itself.  `exps` counts the component evaluations
 // (pixels x components) the far-field culling left to do.
 template <int NB, int NX, int NY, bool STORE, bool PREP, int TEAM = 1, int TM = 0>
 __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restrict__ scratch,
                                             const float* __restrict__ d, const float* __restrict__ w,
                                             float* __restrict__ model_out, int lane, int tw = 0,
-                                            unsigned* exps = nullptr, uint32_t tmem = 0, const float* team_ct = nullptr) {
+                                            unsigned* exps = nullptr, uint32_t tmem = 0) {
+    static_assert(TEAM == 1, "whole-warp passes only");
     using G = Geo<NX>;
     using T = Tab<NB>;
     using R = Rows<NY, TEAM>;
@@ -1030,9 +1030,8 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
             float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
             if (cf.fast) {
                 LaneK<NB> lk;
-                if (TEAM == 1) coop_consts<NB, NX>(lk, ct, cf, lane, pan);
-                else read_consts<NB, NX>(lk, team_ct + pan * Scratch<NB, NX, NY, TEAM>::CT, cf, lane, pan);   // team_consts wrote it
-                if (TEAM == 1) {
+                coop_consts<NB, NX>(lk, ct, cf, lane, pan);
+                {
                     // contiguous steps: the pointers run through the segments
                     StepPtrs sp{rt + b * T::RS, d + off0, w + off0, STORE ? model_out + off0 : nullptr,
                                 tmem + (uint32_t)((half * G::PANELS + pan) * STEPS * TM_STEP), 0.f};
@@ -1046,17 +1045,6 @@ __device__ __forceinline__ double warp_chi2(const Coef<NB>& cf, float* __restric
                         row_steps_fast<NB, NX, NY, STORE, PREP, 2, TM>(cf, lk, s0, s1, i, nhi1, sp);
                         row_steps_fast<NB, NX, NY, STORE, PREP, 1, TM>(cf, lk, s0, s1, i, whi1, sp);
                         row_steps_fast<NB, NX, NY, STORE, PREP, 0, TM>(cf, lk, s0, s1, i, STEPS, sp);
-                    }
-                } else {
-                    // a team member owns only STEPS/TEAM steps (no culling in teams): one dense step at a time;
-                    // its table holds just those blocks
-#pragma unroll 1
-                    for (int mth = 0; mth < STEPS / TEAM; ++mth) {
-                        const int so = (mth * TEAM + tw) * G::RG * NX;
-                        StepPtrs sp{rt + (mth * G::BPS + b) * T::RS, d + off0 + so, w + off0 + so,
-                                    STORE ? model_out + off0 + so : nullptr, 0u, 0.f};
-                        int i = 0;
-                        row_steps_fast<NB, NX, NY, STORE, PREP, 2>(cf, lk, s0, s1, i, 1, sp);
                     }
                 }
             } else {
