@@ -397,7 +397,18 @@ def run_b200(a):
         # (sampler.ChainStreamer, K3): the chain rows of batch i travel to pinned host memory on the
         # copy stream while batch i+1 is uploaded, prepared and sampled.  Every copy of every step is
         # inside the timed region; the number is total wall time / steps.
-        streamer = sampler.ChainStreamer(smp, U)
+        #
+        # Two sampler handles (each with its pixel domain, chain streamer and compute stream) take the
+        # batches in turn: upload, frame prep and initial chi-square of batch i+1 -- and the first
+        # CTAs of its sampler kernel -- run while the last CTAs of batch i finish (the persistent kernel
+        # holds every SM, so nothing of the NEXT batch can start on the same stream before it ends).
+        dom_b, smp_b = make_sampler()
+        smp_b.set_chain_format("f32delta")
+        doms, smps = [dom, dom_b], [smp, smp_b]
+        streamers = [sampler.ChainStreamer(smp, U), sampler.ChainStreamer(smp_b, U)]
+        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        for st_ in streams:
+            st_.wait_stream(torch.cuda.current_stream(dev))
         tot_hs = [torch.empty((2 * P + 1,), dtype=torch.int64).pin_memory() for _ in range(2)]
         got_rows = 0
 
@@ -411,45 +422,51 @@ def run_b200(a):
 
         def stream_step(i):
             j = i & 1
-            compute = torch.cuda.current_stream(dev)
+            compute, streamer = streams[j], streamers[j]
             up_stream.wait_event(consumed[j])              # the batch two steps ago has been read out of this pair
             with torch.cuda.stream(up_stream):
                 fr_d[j].copy_(frames_h, non_blocking=True)
                 in_d[j].copy_(init_h, non_blocking=True)
                 uploaded[j].record(up_stream)
-            compute.wait_event(uploaded[j])
-            frame.prepare_domain(fr_d[j], HEADER, origin=origins, nbody=a.nbody, into=dom)
-            smp.reset(in_d[j], seed=a.seed + 100 + i)
-            consumed[j].record(compute)
-            prev = streamer.run(U)
-            stt = smp.stats(moments=False)
-            tot_d = torch.cat([stt["tries"], stt["accepts"], stt["min_tries"].reshape(1)])
-            # the counters leave on the copy stream too: a device->host copy queued on the compute stream would wait
-            # behind the chain rows of this batch (one copy engine per direction) and hold up the next batch
-            streamer.copy_stream.wait_stream(compute)
-            with torch.cuda.stream(streamer.copy_stream):
-                tot_hs[j].copy_(tot_d, non_blocking=True)
-            tot_d.record_stream(streamer.copy_stream)
+            with torch.cuda.stream(compute):
+                compute.wait_event(uploaded[j])
+                frame.prepare_domain(fr_d[j], HEADER, origin=origins, nbody=a.nbody, into=doms[j])
+                smps[j].reset(in_d[j], seed=a.seed + 100 + i)
+                consumed[j].record(compute)
+                prev = streamer.run(U)
+                stt = smps[j].stats(moments=False)
+                tot_d = torch.cat([stt["tries"], stt["accepts"], stt["min_tries"].reshape(1)])
+                # the counters leave on the copy stream too: a device->host copy queued on the compute stream would wait
+                # behind the chain rows of this batch (one copy engine per direction) and hold up the next batch
+                streamer.copy_stream.wait_stream(compute)
+                with torch.cuda.stream(streamer.copy_stream):
+                    tot_hs[j].copy_(tot_d, non_blocking=True)
+                tot_d.record_stream(streamer.copy_stream)
             return 0 if prev is None else prev.shape[0]
 
-        stream_step(0)                      # warm-up (allocations, first touch of the pinned buffers)
-        streamer.finish()
+        stream_step(0)                      # warm-up of both handles (allocations, first touch of the pinned buffers)
+        stream_step(1)
+        for sr in streamers:
+            sr.finish()
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
         marks = [t0]
         for i in range(n_e2e):
-            got_rows += stream_step(i + 1)
-            marks.append(time.perf_counter())      # batch i has arrived in pinned host memory
-        last = streamer.finish()
-        got_rows += 0 if last is None else last.shape[0]
+            got_rows += stream_step(i + 2)
+            marks.append(time.perf_counter())      # a batch has arrived in pinned host memory
+        for sr in (streamers[n_e2e & 1], streamers[1 - (n_e2e & 1)]):       # the two batches still on their way, oldest first
+            last = sr.finish()
+            got_rows += 0 if last is None else last.shape[0]
         torch.cuda.synchronize()
         dist.barrier()
         t_total = (time.perf_counter() - t0) / n_e2e
         assert got_rows == rows * n_e2e, (got_rows, rows, n_e2e)
         # wall clock on a shared host is noisy (single steps of several 100 ms occur): the headline is
         # the MEDIAN interval between the arrivals of consecutive batches, the mean is reported too
-        gaps = [b - a_ for a_, b in zip(marks[1:-1], marks[2:])]
+        # (the first two timed steps hand nothing back -- each handle's first batch is still on its way)
+        first = 3 if len(marks) > 6 else 1
+        gaps = [b - a_ for a_, b in zip(marks[first:-1], marks[first + 1:])]
         if os.environ.get("LAPF_BENCH_DEBUG"):
             sys.stderr.write("e2e stream arrival gaps (ms): %s\n" % ["%.1f" % (1e3 * t) for t in gaps])
         t_stream = float(dist.allreduce_max(torch.tensor([statistics.median(gaps)], dtype=torch.float64, device=dev)).item())
@@ -461,7 +478,9 @@ def run_b200(a):
         e2e = {"value": float(W) * U * world * S * S / t_stream, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * t_stream, "ms_per_step_mean": 1e3 * t_total, "steps": n_e2e,
-               "what": "a stream of batches through the public API: per step pinned host frames + starting "
+               "handles": 2,
+               "what": "a stream of batches through the public API, taken in turn by two sampler handles on two "
+                       "streams (the preparation of batch i+1 runs in the tail of batch i): per step pinned host frames + starting "
                        "points -> H2D (own stream, double-buffered) -> frame prep (mask, noise map) -> sampler reset (initial chi-square) -> "
                        "%d updates -> chain rows + counters D2H to pinned host, the chain rows double-buffered on "
                        "a copy stream (ChainStreamer) so they overlap the next batch; wall clock between the "

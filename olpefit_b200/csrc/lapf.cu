@@ -323,6 +323,7 @@ struct RunArgs {
     double sk_inv_sep, sk_inv_pa;   // 1 / bin width
     int sk_bins, chain_f32;
     double* probe;               // self-test only: [rows][W][3] = parameter index, proposed value, TRIAL chi-square
+    unsigned long long* cta_times;   // diagnosis only (LAPF_CTA_TIMES): [CTAs][3] = start, end (globaltimer ns), SM id
     int64_t n_walkers;
     int64_t t0, n_updates;       // first update index, updates in this launch
     int64_t next_record;         // first count >= t0+1 at which a row is recorded
@@ -611,6 +612,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
         // ---- one walker per lane: draws, proposal, coefficients of the trial vector -------------
         int k = 0;
         double nv = 0.0, lnu = 0.0;
+        bool skip = false;
         if (mine) {
             const Draw dr = make_draw(a.seed, gid, (uint64_t)(a.t0 + u), P);   // apf_step2.py:302, :64/:68, :143
             const double oxd = (double)((two && slot) ? ox1 : ox0), oyd = (double)((two && slot) ? oy1 : oy0);
@@ -637,7 +639,13 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
             set_fast_serial<NB, NX, NY>(cf);
             if (a.plain) cf.fast = false;
             if (NX >= 64 && a.cull) set_cull_serial<NB, NX, NY>(cf); else no_cull<NB, NX, NY>(cf);
-            store_coef<NB, Geo<NX>::PANELS>(img + lane * I::STRIDE, cf, slot);
+            // A proposal that is nan by construction (log10 of a negative value, apf_step2.py:66-70: a start
+            // with a negative background never moves it) has chi-square nan and is rejected (:139-148): its
+            // pass is skipped instead of sending a nan vector through the plain loop at twice the cost of a
+            // pass.  (With two vectors per pass it keeps its partner company in the factorised loop instead.)
+            skip = nv != nv;
+            if (skip && WPP > 1) cf.fast = true;
+            store_coef<NB, Geo<NX>::PANELS>(img + lane * I::STRIDE, cf, slot | (skip ? 2 : 0));
         }
         __syncwarp();
 
@@ -649,9 +657,10 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
                 Coef<NB> cf;
                 int sl = 0;
                 load_coef<NB, Geo<NX>::PANELS>(cf, img + i * I::STRIDE, &sl);
+                if (sl & 2) continue;                   // a nan proposal: no pass (uniform: the image is the warp's)
                 unsigned e_upd = 0;
                 const double c = warp_chi2<NB, NX, NY, false, true, 1, TM>(cf, rt, sd, sw, nullptr, lane, 0, &e_upd,
-                                                                           TM == 1 ? tmem + (uint32_t)sl * slot_cols : tmem);   // :314-316
+                                                                           TM == 1 ? tmem + (uint32_t)(sl & 1) * slot_cols : tmem);   // :314-316
                 if (lane == i) { chi_t = c; n_exps += e_upd; }
             }
         } else {
@@ -666,7 +675,8 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
                     Coef<NB> cf;
                     int sl = 0;
                     load_coef<NB, 1>(cf, img + mine_i * I::STRIDE, &sl);
-                    sl = __shfl_sync(kFull, sl, 0);
+                    if (__all_sync(kFull, (sl & 2) != 0)) continue;      // both are nan proposals: no pass
+                    sl = __shfl_sync(kFull, sl, 0) & 1;
                     unsigned e_upd = 0;
                     const double c = warp_chi2_pair<NB, NX, NY, false, true, TM>(cf, rt, sd, sw, nullptr, lane, &e_upd,
                                                                                  tmem + (uint32_t)sl * slot_cols);   // :314-316
@@ -681,6 +691,7 @@ __device__ __forceinline__ void run_batch(const RunArgs& a, const float* sd, con
 
         // ---- one walker per lane: accept / reject, counters, chain row --------------------------
         if (mine) {
+            if (skip) chi_t = nan("");
             if (a.outside) {
                 double fl = st[a.floor_index];
                 if (k == a.floor_index) fl = nv;
@@ -760,6 +771,14 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
     if (TM) tmem_fence_after_sync();
     const uint32_t tmem_base = TM ? tmem_slot : 0u;
 
+    if (a.cta_times && threadIdx.x == 0) {
+        unsigned long long t;
+        unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        a.cta_times[3 * blockIdx.x] = t;
+        a.cta_times[3 * blockIdx.x + 2] = sm;
+    }
     const int i0 = a.cta_item[blockIdx.x], i1 = a.cta_item[blockIdx.x + 1];
     int cur_frame[2] = {-1, -1};
     uint32_t phase = 0;
@@ -807,6 +826,11 @@ __global__ void __launch_bounds__(NW * 32, 1) gibbs_batch_kernel(const __grid_co
         tmem_fence_before_sync();
         __syncthreads();
         if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
+    }
+    if (a.cta_times && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.cta_times[3 * blockIdx.x + 1] = t;
     }
 }
 
@@ -1736,6 +1760,7 @@ static void fill_run_args(const lapf_sampler* s, RunArgs& a, int64_t n_updates, 
     a.cull = cull_enabled(&pb);
     a.plain = plain_loop(&pb);
     a.probe = nullptr;
+    a.cta_times = nullptr;
 }
 
 int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, void* chain_out, int64_t rows_cap, void* stream) {
@@ -1748,7 +1773,24 @@ int lapf_sampler_run(lapf_sampler* s, int64_t n_updates, void* chain_out, int64_
         return fail(LAPF_ERR_INVALID, "chain_out holds %lld rows but this run records %lld", (long long)rows_cap, (long long)rows);
     RunArgs a;
     fill_run_args(s, a, n_updates, chain_out);
+    // diagnosis (LAPF_CTA_TIMES=<file>): start, end and SM of every CTA of the batched kernel, one text line per launch
+    const char* times_path = s->team == 1 ? getenv("LAPF_CTA_TIMES") : nullptr;
+    if (times_path) CU(cudaMalloc((void**)&a.cta_times, sizeof(unsigned long long) * 3 * s->launch_grid));
     int rc = launch_dispatch(s, a, (cudaStream_t)stream);
+    if (times_path) {
+        std::vector<unsigned long long> h((size_t)3 * s->launch_grid);
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaMemcpy(h.data(), a.cta_times, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
+        cudaFree(a.cta_times);
+        if (FILE* f = fopen(times_path, "a")) {
+            unsigned long long t0 = ~0ull;
+            for (int b = 0; b < s->launch_grid; ++b) t0 = std::min(t0, h[3 * b]);
+            for (int b = 0; b < s->launch_grid; ++b)
+                fprintf(f, "%llu:%llu:%llu ", h[3 * b] - t0, h[3 * b + 1] - t0, h[3 * b + 2]);
+            fprintf(f, "\n");
+            fclose(f);
+        }
+    }
     if (rc) return rc;
     s->count += n_updates;
     s->launches++;
