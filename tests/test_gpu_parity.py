@@ -279,6 +279,32 @@ def test_sampler_negative_log_parameter_is_never_accepted(gpu):
     assert accepts[0].sum() > 0 and np.isfinite(st[0, -1])
 
 
+@pytest.mark.parametrize("size", [32, 64])
+def test_nan_proposals_cost_no_pass_and_change_nothing(gpu, size):
+    """The batched kernel skips the pass of a proposal that is nan by construction (DESIGN.md section
+    4).  Walkers with a negative log-proposed parameter sit between walkers without (on 32-pixel
+    stamps they share passes with them): the parameter never moves, every other one does, the state's
+    chi-square is the stateless operator's bit for bit, and every chain is the chain the walker has
+    when it runs alone."""
+    torch = gpu["torch"]
+    dom, stamps, origins, p0 = _sampler_setup(gpu, 2, size)
+    walkers = 71
+    init = np.tile(p0, (walkers, 1))
+    neg = np.arange(walkers) % 2 == 0
+    init[neg, 9] = -2.5                               # background: log10-proposed (apf_step2.py:217), negative start
+    with gpu["sampler"].GibbsSampler(dom, init, seed=9, id_base=300, team_warps=1) as s:
+        chain = s.run(200)
+        st, tries, accepts = (t.cpu().numpy() for t in s.state())
+    assert (tries[neg, 9] > 0).all() and (accepts[neg, 9] == 0).all() and (st[neg, 9] == -2.5).all()
+    assert accepts[~neg, 9].sum() > 0
+    assert (accepts.sum(axis=1) > 5).all() and np.isfinite(st[:, -1]).all()
+    _, c = dom.model_chi2(np.ascontiguousarray(st[:, :-1]))
+    assert np.array_equal(c.cpu().numpy(), st[:, -1])
+    for w in (0, 1, 36, 69, 70):
+        with gpu["sampler"].GibbsSampler(dom, init[w:w + 1], seed=9, id_base=300 + w, team_warps=1) as s:
+            assert torch.equal(chain[:, w], s.run(200)[:, 0]), "walker %d" % w
+
+
 def test_sampler_moments_match_chain(gpu):
     dom, stamps, origins, p0 = _sampler_setup(gpu, 2, 32, n_frames=2)
     walkers = 20
